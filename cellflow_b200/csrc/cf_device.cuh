@@ -1,0 +1,108 @@
+// cf_device.cuh — constants and small device helpers shared by every kernel of the engine.
+//
+// Arithmetic contract: everything that decides a neighbour — displacement,
+// minimum-image wrap, squared distance — uses exactly the rounding points of the reference as
+// nvcc compiles it for sm_100a (ParticleSimulation.cu:92-112): d = o - p, exact wrap by +-W,
+// d2 = fma(dz,dz, fma(dx,dx, dy*dy)).  Those are written with the __f*_rn intrinsics, which the
+// compiler never contracts or reorders.  The comparison "sqrtf(d2 + 1e-4f) < Reff" is replaced
+// by the equivalent "d2 < cut2[type pair]" with cut2 computed exactly on the host (tables.cpp).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define CF_T_MAX 10
+#define CF_TT_MAX (CF_T_MAX * CF_T_MAX)
+
+// Per-step constants, passed to kernels by value.
+struct StepConst {
+    float W[3];      // canvasWidth, canvasHeight, canvasDepth
+    float halfW[3];  // W * 0.5f   (reference: ParticleSimulation.cu:97-102)
+    float nhalfW[3]; // W * -0.5f
+    float inv[3];    // (float)dims / W      — cell index = min((int)(pos * inv), dims - 1)
+    int dims[3];     // cells per axis; linear cell = (cx * dims[1] + cy) * dims[2] + cz
+    int periodic_x;  // 0 when x is slab-decomposed (ghost layers replace the wrap)
+    int T;
+    float repulsion, attraction;
+    float nk_log2e;  // -k * log2(e): exp(-k r^2) = exp2(nk_log2e * r^2)
+    float dt, friction;
+    float one_minus_balance, force_multiplier, max_expected; // .cu:136-143
+    int uniform_radius; // 1 when every type pair has the same cut2 (all shipped presets)
+    float cut2_uniform, inv_reff_uniform;
+};
+
+// Device tables (global memory, staged into shared memory by the kernels that index them):
+//   [0      , TT)   cut2    : accept iff d2 < cut2[ti*T+tj]
+//   [TT     , 2TT)  invReff : 1 / Reff[ti*T+tj]
+//   [2TT    , 3TT)  force   : forceTable[ti*T+tj]  (row = self, column = other; .cu:116)
+struct DeviceTables {
+    float cut2[CF_TT_MAX];
+    float inv_reff[CF_TT_MAX];
+    float force[CF_TT_MAX];
+};
+
+__device__ __forceinline__ int cf_cell_coord(float x, float inv, int n) {
+    int c = (int)__fmul_rn(x, inv);
+    c = c > n - 1 ? n - 1 : c;
+    return c < 0 ? 0 : c;
+}
+
+__device__ __forceinline__ uint32_t cf_cell_key(float4 p, const StepConst& c) {
+    int cx = cf_cell_coord(p.x, c.inv[0], c.dims[0]);
+    int cy = cf_cell_coord(p.y, c.inv[1], c.dims[1]);
+    int cz = cf_cell_coord(p.z, c.inv[2], c.dims[2]);
+    return (uint32_t)((cx * c.dims[1] + cy) * c.dims[2] + cz);
+}
+
+// Minimum-image wrap exactly as the reference: two dependent tests (.cu:97-98).  Both
+// additions are exact in fp32 (Sterbenz), so any formulation of the same decision is bit-equal.
+__device__ __forceinline__ float cf_wrap(float d, float W, float half, float nhalf) {
+    d = d > half ? __fsub_rn(d, W) : d;
+    d = d < nhalf ? __fadd_rn(d, W) : d;
+    return d;
+}
+
+__device__ __forceinline__ float cf_dist2(float dx, float dy, float dz) {
+    return __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
+}
+
+__device__ __forceinline__ float cf_ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float cf_rsqrt(float x) {
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// Accepted-pair force term (ParticleSimulation.cu:113-131), fast-intrinsic form:
+//   dist = sqrt(d2 + 1e-4), r = dist / Reff, net = (rep * exp(-k r^2) - att * r) * fv,
+//   F += (d / dist) * net.
+// MUFU.RSQ / MUFU.EX2 replace the IEEE sqrt, the four IEEE divides and expf of the reference;
+// each is within 2 ulp, far inside the 1e-5 force tolerance (tests/test_parity_gpu.py).
+__device__ __forceinline__ void cf_pair_force(float dx, float dy, float dz, float d2, float inv_reff,
+                                              float fv, const StepConst& c, float& fx, float& fy,
+                                              float& fz) {
+    float x = __fadd_rn(d2, 0.0001f);
+    float rinv = cf_rsqrt(x);
+    float dist = x * rinv;
+    float r = dist * inv_reff;
+    float e = cf_ex2(r * r * c.nk_log2e);
+    float net = fmaf(e, c.repulsion, -(r * c.attraction));
+    float s = fv * net * rinv;
+    fx = fmaf(s, dx, fx);
+    fy = fmaf(s, dy, fy);
+    fz = fmaf(s, dz, fz);
+}
+
+// Counter-based generator of cf_init_particles (restated in oracle/cellflow_oracle.c).
+__host__ __device__ __forceinline__ uint64_t cf_mix64(uint64_t z) {
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+__host__ __device__ __forceinline__ float cf_u01(uint64_t h) {
+    return (float)(h >> 40) * 5.9604644775390625e-08f;
+}

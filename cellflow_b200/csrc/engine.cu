@@ -1,0 +1,974 @@
+// engine.cu — the cf_sim handle and the C ABI of include/cellflow_b200.h.
+//
+// Replaces the reference's host class ParticleSimulation (cuda-native/src/ParticleSimulation.cu:
+// 426-687).  One handle = one device, one non-default stream, device-resident float4 SoA state
+// kept in cell-sorted order between steps.  A step is
+//     cell key -> stable radix sort -> reorder -> cell bounds -> pair force -> fused integrate
+// with no host synchronisation inside (the reference synchronises after every launch, .cu:553).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/cellflow_b200.h"
+#include "cf_device.cuh"
+#include "kernels_force.cuh"
+#include "kernels_graph.cuh"
+#include "kernels_sort.cuh"
+#include "kernels_state.cuh"
+#include "kernels_tile.cuh"
+
+static_assert(sizeof(AosParticle) == 44 && sizeof(cf_particle) == 44, "reference Particle is 44 B");
+
+// ---------------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CU(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess)                                                                \
+            return fail(CF_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_),  \
+                        __FILE__, __LINE__);                                                  \
+    } while (0)
+#define ARG(cond)                                                                             \
+    do {                                                                                      \
+        if (!(cond)) return fail(CF_ERR_ARG, "bad argument: %s (%s:%d)", #cond, __FILE__, __LINE__); \
+    } while (0)
+
+extern "C" const char* cf_last_error(void) { return g_err; }
+extern "C" const char* cf_version(void) { return "cellflow_b200 0.1 (sm_100a)"; }
+
+// ---------------------------------------------------------------------------------------------
+// handle
+// ---------------------------------------------------------------------------------------------
+struct StepEvents {
+    cudaEvent_t e[5]; // begin, after sort, after force, after integrate, (spare)
+};
+
+struct cf_sim {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int n = 0;   // owned particles
+    int cap = 0; // slot capacity
+    int T = 6;
+    cf_params params;
+    float raw[CF_TT_MAX];
+    float radio[CF_T_MAX];
+    float force[CF_TT_MAX];
+    bool force_overridden = false;
+
+    float4* pos[2] = {nullptr, nullptr};
+    float4* vel[2] = {nullptr, nullptr};
+    int* id[2] = {nullptr, nullptr};
+    float4* frc = nullptr;
+    int cur = 0;
+    uint32_t* keys[2] = {nullptr, nullptr};
+    uint32_t* vals[2] = {nullptr, nullptr};
+    uint32_t* hist = nullptr;
+    size_t hist_cap = 0;
+    int* cell_start = nullptr;
+    size_t cell_cap = 0;
+    DeviceTables* d_tables = nullptr;
+    StepConst sc;
+    int ncell = 0;
+    bool sorted_valid = false;
+
+    int2* edges = nullptr;
+    int2* edge_slots = nullptr;
+    int edge_cap = 0;
+    int* d_edge_count = nullptr;
+    int n_edges = 0;
+
+    AosParticle* d_aos = nullptr;
+    int* d_counts = nullptr;
+    unsigned long long* d_accum = nullptr;
+
+    // options
+    int opt_stencil = 0;     // reserved (0 = automatic)
+    int opt_force_kernel = 0; // 0 auto, 1 per-particle, 2 tile
+    int opt_timing = 0;
+    double opt_max_cells_per_particle = 0.5;
+
+    // stats
+    std::vector<StepEvents> ev_pool;
+    size_t ev_used = 0;
+    cudaEvent_t ev_g0 = nullptr, ev_g1 = nullptr;
+    bool graph_timed = false;
+    double ms_sort = 0, ms_force = 0, ms_integrate = 0, ms_total = 0, ms_graph = 0;
+    long long stat_steps = 0;
+    long long launches = 0;
+    long long tested_pairs = 0;
+    int last_force_kernel = 0;
+};
+
+#define LAUNCH(sim, kernel, grid, block, smem, ...)                         \
+    do {                                                                    \
+        kernel<<<(grid), (block), (smem), (sim)->stream>>>(__VA_ARGS__);    \
+        (sim)->launches++;                                                  \
+    } while (0)
+
+static inline int div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+static int set_device(const cf_sim* sim) {
+    CU(cudaSetDevice(sim->device));
+    return 0;
+}
+
+static void free_particle_buffers(cf_sim* s) {
+    for (int b = 0; b < 2; b++) {
+        cudaFree(s->pos[b]);
+        cudaFree(s->vel[b]);
+        cudaFree(s->id[b]);
+        cudaFree(s->keys[b]);
+        cudaFree(s->vals[b]);
+        s->pos[b] = s->vel[b] = nullptr;
+        s->id[b] = nullptr;
+        s->keys[b] = s->vals[b] = nullptr;
+    }
+    cudaFree(s->frc);
+    cudaFree(s->d_aos);
+    cudaFree(s->d_counts);
+    cudaFree(s->edges);
+    cudaFree(s->edge_slots);
+    s->frc = nullptr;
+    s->d_aos = nullptr;
+    s->d_counts = nullptr;
+    s->edges = s->edge_slots = nullptr;
+    s->edge_cap = 0;
+    s->cap = 0;
+}
+
+static int alloc_particle_buffers(cf_sim* s, int cap) {
+    free_particle_buffers(s);
+    size_t c = (size_t)std::max(cap, 1);
+    for (int b = 0; b < 2; b++) {
+        CU(cudaMalloc(&s->pos[b], c * sizeof(float4)));
+        CU(cudaMalloc(&s->vel[b], c * sizeof(float4)));
+        CU(cudaMalloc(&s->id[b], c * sizeof(int)));
+        CU(cudaMalloc(&s->keys[b], c * sizeof(uint32_t)));
+        CU(cudaMalloc(&s->vals[b], c * sizeof(uint32_t)));
+    }
+    CU(cudaMalloc(&s->frc, c * sizeof(float4)));
+    CU(cudaMalloc(&s->d_aos, c * sizeof(AosParticle)));
+    CU(cudaMalloc(&s->d_counts, c * sizeof(int)));
+    for (int b = 0; b < 2; b++) {
+        CU(cudaMemsetAsync(s->pos[b], 0, c * sizeof(float4), s->stream));
+        CU(cudaMemsetAsync(s->vel[b], 0, c * sizeof(float4), s->stream));
+        CU(cudaMemsetAsync(s->id[b], 0, c * sizeof(int), s->stream));
+    }
+    CU(cudaMemsetAsync(s->frc, 0, c * sizeof(float4), s->stream));
+    s->cap = (int)c;
+    s->cur = 0;
+    s->sorted_valid = false;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// tables: force-table squash, per-pair radius, exact cut-off thresholds
+// ---------------------------------------------------------------------------------------------
+
+// updateForceTable, ParticleSimulation.cu:521-527: float tanh, separate product and sum.
+static void squash_force_table(cf_sim* s, float range, float bias, float offset) {
+    for (int i = 0; i < s->T * s->T; i++) {
+        volatile float t = tanhf(s->raw[i] * offset);
+        volatile float v = t * range;
+        v = v + bias;
+        s->force[i] = fmaxf(-1.0f, fminf(1.0f, v));
+    }
+    s->force_overridden = false;
+}
+
+// libc rand() tables of a fresh reference object (.cu:513-519, 533-539).  The reference never
+// calls srand, so its first construction sees the default sequence; this library must not
+// disturb the host's generator, so it replays glibc's TYPE_3 additive feedback generator
+// (seed 1) privately.
+struct GlibcRand {
+    int32_t r[344 + 4096];
+    int k = 0;
+    GlibcRand() {
+        r[0] = 1;
+        for (int i = 1; i < 31; i++) {
+            long long v = (16807LL * r[i - 1]) % 2147483647LL;
+            if (v < 0) v += 2147483647LL;
+            r[i] = (int32_t)v;
+        }
+        for (int i = 31; i < 34; i++) r[i] = r[i - 31];
+        for (int i = 34; i < 344; i++) r[i] = (int32_t)((uint32_t)r[i - 31] + (uint32_t)r[i - 3]);
+        k = 344;
+    }
+    int next() {
+        if (k >= 344 + 4096) k = 344; // never reached by the table draws
+        r[k] = (int32_t)((uint32_t)r[k - 31] + (uint32_t)r[k - 3]);
+        int out = (int)(((uint32_t)r[k]) >> 1);
+        k++;
+        return out;
+    }
+};
+
+static void default_tables(cf_sim* s, GlibcRand& g) {
+    for (int i = 0; i < s->T * s->T; i++) s->raw[i] = (float)g.next() / 2147483647 * 2.0f - 1.0f;
+    squash_force_table(s, 0.28f, -0.20f, 1.0f); // .cu:518
+    for (int i = 0; i < s->T; i++) s->radio[i] = (float)g.next() / 2147483647 * 2.0f - 1.0f;
+}
+
+extern "C" int cf_reference_default_tables(int T, float* raw, float* radio, float* effective) {
+    ARG(T >= 1 && T <= CF_MAX_PARTICLE_TYPES && raw && radio && effective);
+    cf_sim tmp;
+    tmp.T = T;
+    GlibcRand g;
+    default_tables(&tmp, g);
+    memcpy(raw, tmp.raw, sizeof(float) * T * T);
+    memcpy(radio, tmp.radio, sizeof(float) * T);
+    memcpy(effective, tmp.force, sizeof(float) * T * T);
+    return CF_OK;
+}
+
+// Reff of a type pair as the reference kernel evaluates it (.cu:108-110, SASS rounding points):
+//   a_x = fma(radio[x], ratio, 1);  Reff = fma(a_p, radius, a_o * radius) * 0.5
+static float reff_pair(const cf_sim* s, int tp, int to) {
+    float ap = fmaf(s->radio[tp], s->params.ratioWithLFO, 1.0f);
+    float ao = fmaf(s->radio[to], s->params.ratioWithLFO, 1.0f);
+    volatile float prod = ao * s->params.radius;
+    return fmaf(ap, s->params.radius, prod) * 0.5f;
+}
+
+// Largest-accepting threshold: the reference accepts iff sqrtf(d2 + 1e-4f) < Reff.  sqrtf and
+// the addition are monotone, so there is a float cut2 with  accept <=> d2 < cut2 ; it is found
+// here exactly (host sqrtf is IEEE, like the device's sqrt.rn).
+static float exact_cut2(float reff) {
+    if (!(reff > 0.0f)) return 0.0f;         // nothing is closer than sqrt(1e-4) ... or NaN
+    if (std::isinf(reff)) return INFINITY;
+    // c1 = smallest x with sqrtf(x) >= reff
+    float c1 = reff * reff;
+    while (sqrtf(c1) >= reff && c1 > 0.0f) c1 = nextafterf(c1, 0.0f);
+    while (!(sqrtf(c1) >= reff)) c1 = nextafterf(c1, INFINITY);
+    if (std::isinf(c1)) return INFINITY;
+    // c2 = smallest d >= 0 with (d + 1e-4f) >= c1
+    float c2 = c1 - 0.0001f;
+    if (!(c2 > 0.0f)) c2 = 0.0f;
+    auto ge = [&](float d) { volatile float x = d + 0.0001f; return x >= c1; };
+    while (c2 > 0.0f && ge(c2)) c2 = nextafterf(c2, 0.0f);
+    while (!ge(c2)) c2 = nextafterf(c2, INFINITY);
+    return c2;
+}
+
+static float compute_tables(cf_sim* s, DeviceTables& t, bool& uniform) {
+    float rmax = 0.f;
+    int T = s->T;
+    for (int a = 0; a < T; a++)
+        for (int b = 0; b < T; b++) {
+            float reff = reff_pair(s, a, b);
+            t.cut2[a * T + b] = exact_cut2(reff);
+            t.inv_reff[a * T + b] = reff > 0.f ? 1.0f / reff : 0.f;
+            t.force[a * T + b] = s->force[a * T + b];
+            if (reff > rmax) rmax = reff;
+        }
+    uniform = true;
+    for (int i = 1; i < T * T; i++)
+        if (t.cut2[i] != t.cut2[0] || t.inv_reff[i] != t.inv_reff[0]) uniform = false;
+    return rmax;
+}
+
+// Chooses the cell grid for the current parameters and uploads the tables.
+static int prepare_step_const(cf_sim* s) {
+    const cf_params& p = s->params;
+    ARG(p.canvasWidth > 0.f && p.canvasHeight > 0.f && p.canvasDepth > 0.f);
+    ARG(p.numParticleTypes == s->T);
+    DeviceTables t;
+    memset(&t, 0, sizeof(t));
+    bool uniform = true;
+    float rmax = compute_tables(s, t, uniform);
+    StepConst c;
+    memset(&c, 0, sizeof(c));
+    float W[3] = {p.canvasWidth, p.canvasHeight, p.canvasDepth};
+    // cell edge >= R_max (1e-5 margin covers the rounding of pos * inv), and coarse enough that
+    // the grid has at most opt_max_cells_per_particle * n cells
+    double vol = (double)W[0] * W[1] * W[2];
+    double max_cells = std::max(64.0, s->opt_max_cells_per_particle * (double)std::max(s->n, 1));
+    max_cells = std::min(max_cells, 16777216.0);
+    double edge = std::max((double)rmax * (1.0 + 1e-5), cbrt(vol / max_cells));
+    if (!(edge > 0.0)) edge = cbrt(vol / max_cells);
+    long long ncell = 1;
+    for (int a = 0; a < 3; a++) {
+        int d = (int)floor((double)W[a] / edge);
+        d = std::max(1, std::min(d, 1024));
+        c.dims[a] = d;
+        c.W[a] = W[a];
+        c.halfW[a] = W[a] * 0.5f;
+        c.nhalfW[a] = W[a] * -0.5f;
+        c.inv[a] = (float)d / W[a];
+        ncell *= d;
+    }
+    c.periodic_x = 1;
+    c.T = s->T;
+    c.repulsion = p.repulsion;
+    c.attraction = p.attraction;
+    c.nk_log2e = -p.k * 1.4426950408889634f;
+    c.dt = p.delta_t;
+    c.friction = p.friction;
+    c.one_minus_balance = 1.0f - p.balance;
+    c.force_multiplier = p.forceMultiplier;
+    c.max_expected = (float)p.maxExpectedNeighbors;
+    c.uniform_radius = uniform ? 1 : 0;
+    c.cut2_uniform = t.cut2[0];
+    c.inv_reff_uniform = t.inv_reff[0];
+    bool grid_changed = memcmp(c.dims, s->sc.dims, sizeof(c.dims)) != 0 ||
+                        memcmp(c.W, s->sc.W, sizeof(c.W)) != 0;
+    s->sc = c;
+    s->ncell = (int)ncell;
+    if (grid_changed) s->sorted_valid = false;
+    if ((size_t)ncell + 1 > s->cell_cap) {
+        cudaFree(s->cell_start);
+        s->cell_start = nullptr;
+        s->cell_cap = (size_t)ncell + 1 + (size_t)ncell / 4;
+        CU(cudaMalloc(&s->cell_start, s->cell_cap * sizeof(int)));
+    }
+    CU(cudaMemcpyAsync(s->d_tables, &t, sizeof(t), cudaMemcpyHostToDevice, s->stream));
+    // pageable source: the copy is staged before the call returns, `t` may go out of scope
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// cell-list build
+// ---------------------------------------------------------------------------------------------
+static int ensure_sorted(cf_sim* s) {
+    if (s->sorted_valid) return 0;
+    int n = s->n;
+    if (n <= 0) return 0;
+    int cur = s->cur, nxt = cur ^ 1;
+    int blocks = div_up(n, 256);
+    LAUNCH(s, cell_key_kernel, blocks, 256, 0, s->pos[cur], s->keys[0], s->vals[0], n, s->sc);
+    int bits = 1;
+    while ((1ll << bits) < (long long)s->ncell) bits++;
+    int passes = div_up(bits, 8);
+    int bits_per_pass = div_up(bits, passes);
+    int items = 4096;
+    while (div_up(n, items) > 1024) items *= 2;
+    int nblocks = div_up(n, items);
+    size_t hist_need = (size_t)RS_BINS * nblocks;
+    if (hist_need > s->hist_cap) {
+        cudaFree(s->hist);
+        s->hist = nullptr;
+        s->hist_cap = hist_need * 2;
+        CU(cudaMalloc(&s->hist, s->hist_cap * sizeof(uint32_t)));
+    }
+    int src = 0;
+    for (int p = 0; p < passes; p++) {
+        int shift = p * bits_per_pass;
+        uint32_t mask = (1u << bits_per_pass) - 1u;
+        LAUNCH(s, rs_hist_kernel, nblocks, RS_THREADS, 0, s->keys[src], n, shift, mask, s->hist, nblocks, items);
+        LAUNCH(s, rs_scan_kernel, 1, 1024, 0, s->hist, RS_BINS * nblocks);
+        LAUNCH(s, rs_scatter_kernel, nblocks, RS_THREADS, 0, s->keys[src], s->vals[src], s->keys[src ^ 1],
+               s->vals[src ^ 1], n, shift, mask, s->hist, nblocks, items);
+        src ^= 1;
+    }
+    LAUNCH(s, reorder_kernel, blocks, 256, 0, s->vals[src], s->pos[cur], s->vel[cur], s->id[cur],
+           s->pos[nxt], s->vel[nxt], s->id[nxt], n);
+    LAUNCH(s, cell_bounds_kernel, div_up(s->ncell + 1, 256), 256, 0, s->keys[src], n, s->cell_start,
+           s->ncell, 0);
+    if (src != 0) std::swap(s->keys[0], s->keys[1]), std::swap(s->vals[0], s->vals[1]);
+    // keys[0] now holds the sorted keys of the current order
+    s->cur = nxt;
+    s->sorted_valid = true;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// lifetime
+// ---------------------------------------------------------------------------------------------
+extern "C" void cf_default_params(cf_params* p) {
+    if (!p) return;
+    p->radius = 42.07f;
+    p->delta_t = 0.18f;
+    p->friction = 0.51f;
+    p->repulsion = 64.83f;
+    p->attraction = 3.06f;
+    p->k = 29.45f;
+    p->balance = 0.79f;
+    p->canvasWidth = 8000.0f;
+    p->canvasHeight = 8000.0f;
+    p->canvasDepth = 8000.0f;
+    p->spawnRegionSize = 2000.0f;
+    p->numParticleTypes = 6;
+    p->ratioWithLFO = 0.0f;
+    p->forceMultiplier = 2.33f;
+    p->maxExpectedNeighbors = 400;
+    p->forceRange = 0.28f;
+    p->forceBias = -0.20f;
+    p->ratio = 0.0f;
+    p->lfoA = 0.0f;
+    p->lfoS = 0.1f;
+    p->forceOffset = 1.0f;
+}
+
+extern "C" int cf_create(int particle_count, int num_types, int device, cf_sim** out) {
+    ARG(out != nullptr);
+    *out = nullptr;
+    ARG(particle_count >= 0);
+    ARG(num_types >= 1 && num_types <= CF_MAX_PARTICLE_TYPES);
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(CF_ERR_CUDA, "no CUDA device (%s): cellflow_b200 has no CPU path",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    ARG(device >= 0 && device < ndev);
+    CU(cudaSetDevice(device));
+    cf_sim* s = new cf_sim();
+    s->device = device;
+    s->T = num_types;
+    s->n = particle_count;
+    cf_default_params(&s->params);
+    s->params.numParticleTypes = num_types;
+    memset(&s->sc, 0, sizeof(s->sc));
+    memset(s->raw, 0, sizeof(s->raw));
+    memset(s->radio, 0, sizeof(s->radio));
+    memset(s->force, 0, sizeof(s->force));
+    cudaError_t ce = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
+    if (ce != cudaSuccess) {
+        delete s;
+        return fail(CF_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(ce));
+    }
+    int rc = alloc_particle_buffers(s, particle_count);
+    if (rc == 0 && cudaMalloc(&s->d_tables, sizeof(DeviceTables)) != cudaSuccess) rc = fail(CF_ERR_CUDA, "cudaMalloc tables");
+    if (rc == 0 && cudaMalloc(&s->d_edge_count, sizeof(int)) != cudaSuccess) rc = fail(CF_ERR_CUDA, "cudaMalloc");
+    if (rc == 0 && cudaMalloc(&s->d_accum, sizeof(unsigned long long)) != cudaSuccess) rc = fail(CF_ERR_CUDA, "cudaMalloc");
+    if (rc == 0 && cudaEventCreate(&s->ev_g0) != cudaSuccess) rc = fail(CF_ERR_CUDA, "cudaEventCreate");
+    if (rc == 0 && cudaEventCreate(&s->ev_g1) != cudaSuccess) rc = fail(CF_ERR_CUDA, "cudaEventCreate");
+    if (rc != 0) {
+        cf_destroy(s);
+        return rc;
+    }
+    GlibcRand g;
+    default_tables(s, g);
+    *out = s;
+    return CF_OK;
+}
+
+extern "C" int cf_destroy(cf_sim* s) {
+    if (!s) return CF_OK;
+    cudaSetDevice(s->device);
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    free_particle_buffers(s);
+    cudaFree(s->hist);
+    cudaFree(s->cell_start);
+    cudaFree(s->d_tables);
+    cudaFree(s->d_edge_count);
+    cudaFree(s->d_accum);
+    for (auto& ev : s->ev_pool)
+        for (int i = 0; i < 5; i++) cudaEventDestroy(ev.e[i]);
+    if (s->ev_g0) cudaEventDestroy(s->ev_g0);
+    if (s->ev_g1) cudaEventDestroy(s->ev_g1);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+    return CF_OK;
+}
+
+extern "C" int cf_get_particle_count(const cf_sim* s) { return s ? s->n : CF_ERR_ARG; }
+extern "C" int cf_get_num_particle_types(const cf_sim* s) { return s ? s->T : CF_ERR_ARG; }
+
+// setParticleCount (.cu:564-572): reallocate and re-spawn when the count changes.
+extern "C" int cf_set_particle_count(cf_sim* s, int count) {
+    ARG(s && count >= 0);
+    if (count == s->n) return CF_OK;
+    if (int rc = set_device(s)) return rc;
+    CU(cudaStreamSynchronize(s->stream));
+    s->n = count;
+    if (int rc = alloc_particle_buffers(s, count)) return rc;
+    return cf_init_particles(s, 0x5EED0000ull, CF_INIT_SPAWN_CUBE);
+}
+
+// setNumParticleTypes (.cu:574-579): new random tables, particles re-spawned.
+extern "C" int cf_set_num_particle_types(cf_sim* s, int types) {
+    ARG(s && types >= 1 && types <= CF_MAX_PARTICLE_TYPES);
+    s->T = types;
+    s->params.numParticleTypes = types;
+    GlibcRand g;
+    default_tables(s, g);
+    return cf_init_particles(s, 0x5EED0000ull, CF_INIT_SPAWN_CUBE);
+}
+
+// ---------------------------------------------------------------------------------------------
+// tables
+// ---------------------------------------------------------------------------------------------
+extern "C" int cf_regenerate_force_table(cf_sim* s) {
+    ARG(s);
+    static thread_local GlibcRand g; // successive calls continue the sequence like rand() would
+    for (int i = 0; i < s->T * s->T; i++) s->raw[i] = (float)g.next() / 2147483647 * 2.0f - 1.0f;
+    squash_force_table(s, 0.28f, -0.20f, 1.0f);
+    return CF_OK;
+}
+extern "C" int cf_set_raw_force_table(cf_sim* s, const float* raw, int count) {
+    ARG(s && raw && count >= 0);
+    int m = std::min(count, s->T * s->T); // loadPreset writes min(array, T*T) entries
+    memcpy(s->raw, raw, sizeof(float) * m);
+    return CF_OK;
+}
+extern "C" int cf_get_raw_force_table(const cf_sim* s, float* raw, int count) {
+    ARG(s && raw && count >= s->T * s->T);
+    memcpy(raw, s->raw, sizeof(float) * s->T * s->T);
+    return CF_OK;
+}
+extern "C" int cf_update_force_table(cf_sim* s, float range, float bias, float offset) {
+    ARG(s);
+    s->params.forceRange = range;
+    s->params.forceBias = bias;
+    s->params.forceOffset = offset;
+    squash_force_table(s, range, bias, offset);
+    return CF_OK;
+}
+extern "C" int cf_get_force_table(const cf_sim* s, float* eff, int count) {
+    ARG(s && eff && count >= s->T * s->T);
+    memcpy(eff, s->force, sizeof(float) * s->T * s->T);
+    return CF_OK;
+}
+extern "C" int cf_set_force_table(cf_sim* s, const float* eff, int count) {
+    ARG(s && eff && count == s->T * s->T);
+    memcpy(s->force, eff, sizeof(float) * count);
+    s->force_overridden = true;
+    return CF_OK;
+}
+extern "C" int cf_set_radio_by_type(cf_sim* s, const float* radio, int count) {
+    ARG(s && radio && count >= 0);
+    memcpy(s->radio, radio, sizeof(float) * std::min(count, s->T));
+    return CF_OK;
+}
+extern "C" int cf_set_radio_by_type_value(cf_sim* s, int index, float value) {
+    ARG(s);
+    if (index >= 0 && index < s->T) s->radio[index] = value; // out of range: ignored, .cu:616
+    return CF_OK;
+}
+extern "C" int cf_get_radio_by_type(const cf_sim* s, float* radio, int count) {
+    ARG(s && radio && count >= s->T);
+    memcpy(radio, s->radio, sizeof(float) * s->T);
+    return CF_OK;
+}
+extern "C" int cf_rotate_radio_by_type(cf_sim* s) { // .cu:594-600
+    ARG(s);
+    float tmp = s->radio[s->T - 1];
+    for (int i = s->T - 1; i > 0; i--) s->radio[i] = s->radio[i - 1];
+    s->radio[0] = tmp;
+    return CF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// particle state
+// ---------------------------------------------------------------------------------------------
+extern "C" int cf_init_particles(cf_sim* s, uint64_t seed, int mode) {
+    ARG(s && (mode == CF_INIT_SPAWN_CUBE || mode == CF_INIT_UNIFORM));
+    if (int rc = set_device(s)) return rc;
+    if (s->n > 0)
+        LAUNCH(s, init_particles_kernel, div_up(s->n, 256), 256, 0, s->pos[s->cur], s->vel[s->cur], s->frc,
+               s->id[s->cur], s->n, 0, s->T, seed, mode, s->params.canvasWidth, s->params.canvasHeight,
+               s->params.canvasDepth);
+    s->sorted_valid = false;
+    CU(cudaGetLastError());
+    return CF_OK;
+}
+
+static int upload_impl(cf_sim* s, const cf_particle* aos, const int32_t* counts, const int32_t* ids,
+                       int count) {
+    if (int rc = set_device(s)) return rc;
+    if (count > s->cap) {
+        CU(cudaStreamSynchronize(s->stream));
+        if (int rc = alloc_particle_buffers(s, count)) return rc;
+    }
+    s->n = count;
+    if (count == 0) return CF_OK;
+    CU(cudaMemcpyAsync(s->d_aos, aos, sizeof(AosParticle) * (size_t)count, cudaMemcpyHostToDevice, s->stream));
+    int* d_ids = nullptr;
+    if (counts)
+        CU(cudaMemcpyAsync(s->d_counts, counts, sizeof(int) * (size_t)count, cudaMemcpyHostToDevice, s->stream));
+    if (ids) {
+        d_ids = (int*)s->keys[1]; // scratch: the sort is invalidated anyway
+        CU(cudaMemcpyAsync(d_ids, ids, sizeof(int) * (size_t)count, cudaMemcpyHostToDevice, s->stream));
+    }
+    LAUNCH(s, aos_to_soa_kernel, div_up(count, 256), 256, 0, s->d_aos, counts ? s->d_counts : nullptr, d_ids,
+           s->pos[s->cur], s->vel[s->cur], s->frc, s->id[s->cur], count);
+    s->sorted_valid = false;
+    CU(cudaGetLastError());
+    return CF_OK;
+}
+
+extern "C" int cf_upload_particles(cf_sim* s, const cf_particle* aos, int count) {
+    ARG(s && aos && count >= 0);
+    ARG(count == s->n);
+    return upload_impl(s, aos, nullptr, nullptr, count);
+}
+
+extern "C" int cf_upload_particles_ids(cf_sim* s, const cf_particle* aos, const int32_t* counts,
+                                       const int32_t* ids, int count) {
+    ARG(s && (aos || count == 0) && count >= 0);
+    return upload_impl(s, aos, counts, ids, count);
+}
+
+extern "C" int cf_download_particles(cf_sim* s, cf_particle* aos, int count) {
+    ARG(s && aos && count == s->n);
+    if (int rc = set_device(s)) return rc;
+    if (count == 0) return CF_OK;
+    LAUNCH(s, soa_to_aos_kernel, div_up(count, 256), 256, 0, s->pos[s->cur], s->vel[s->cur], s->frc,
+           s->id[s->cur], s->d_aos, s->d_counts, count, 1);
+    CU(cudaMemcpyAsync(aos, s->d_aos, sizeof(AosParticle) * (size_t)count, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    return CF_OK;
+}
+
+extern "C" int cf_download_particles_ids(cf_sim* s, cf_particle* aos, int32_t* counts, int32_t* ids,
+                                         int capacity, int* count) {
+    ARG(s && count);
+    *count = s->n;
+    ARG(capacity >= s->n);
+    if (int rc = set_device(s)) return rc;
+    if (s->n == 0) return CF_OK;
+    LAUNCH(s, soa_to_aos_kernel, div_up(s->n, 256), 256, 0, s->pos[s->cur], s->vel[s->cur], s->frc,
+           s->id[s->cur], s->d_aos, s->d_counts, s->n, 0);
+    if (aos) CU(cudaMemcpyAsync(aos, s->d_aos, sizeof(AosParticle) * (size_t)s->n, cudaMemcpyDeviceToHost, s->stream));
+    if (counts) CU(cudaMemcpyAsync(counts, s->d_counts, sizeof(int) * (size_t)s->n, cudaMemcpyDeviceToHost, s->stream));
+    if (ids) CU(cudaMemcpyAsync(ids, s->id[s->cur], sizeof(int) * (size_t)s->n, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    return CF_OK;
+}
+
+extern "C" int cf_upload_neighbor_counts(cf_sim* s, const int32_t* counts, int count) {
+    ARG(s && counts && count == s->n);
+    if (int rc = set_device(s)) return rc;
+    if (count == 0) return CF_OK;
+    CU(cudaMemcpyAsync(s->d_counts, counts, sizeof(int) * (size_t)count, cudaMemcpyHostToDevice, s->stream));
+    LAUNCH(s, scatter_counts_kernel, div_up(count, 256), 256, 0, s->d_counts, s->id[s->cur], s->vel[s->cur], count);
+    CU(cudaGetLastError());
+    return CF_OK;
+}
+
+extern "C" int cf_download_neighbor_counts(cf_sim* s, int32_t* counts, int count) {
+    ARG(s && counts && count == s->n);
+    if (int rc = set_device(s)) return rc;
+    if (count == 0) return CF_OK;
+    LAUNCH(s, soa_to_aos_kernel, div_up(count, 256), 256, 0, s->pos[s->cur], s->vel[s->cur], s->frc,
+           s->id[s->cur], s->d_aos, s->d_counts, count, 1);
+    CU(cudaMemcpyAsync(counts, s->d_counts, sizeof(int) * (size_t)count, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    return CF_OK;
+}
+
+extern "C" int cf_move_universe(cf_sim* s, float dx, float dy, float dz) {
+    ARG(s);
+    if (int rc = set_device(s)) return rc;
+    if (s->n == 0) return CF_OK;
+    // the reference passes the DEFAULT canvas here (.cu:586-589); the engine uses the live one
+    LAUNCH(s, move_universe_kernel, div_up(s->n, 256), 256, 0, s->pos[s->cur], s->n, dx, dy, dz,
+           s->params.canvasWidth, s->params.canvasHeight, s->params.canvasDepth);
+    s->sorted_valid = false;
+    CU(cudaGetLastError());
+    return CF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// stepping
+// ---------------------------------------------------------------------------------------------
+extern "C" int cf_set_params(cf_sim* s, const cf_params* p) {
+    ARG(s && p);
+    ARG(p->numParticleTypes == s->T);
+    s->params = *p;
+    return CF_OK;
+}
+extern "C" int cf_get_params(const cf_sim* s, cf_params* p) {
+    ARG(s && p);
+    *p = s->params;
+    return CF_OK;
+}
+
+extern "C" float cf_ratio_with_lfo(const cf_params* p, float t) { // CellFlowWidget.cpp:415-421
+    if (!p) return 0.f;
+    if (p->lfoA != 0.0f) {
+        double lfo = (double)p->lfoA * sin(2.0f * M_PI * (double)p->lfoS * (double)t);
+        return (float)((double)p->ratio + lfo);
+    }
+    return p->ratio;
+}
+
+static StepEvents* next_events(cf_sim* s) {
+    if (!s->opt_timing) return nullptr;
+    if (s->ev_used == s->ev_pool.size()) {
+        if (s->ev_pool.size() >= 4096) return nullptr;
+        StepEvents ev;
+        for (int i = 0; i < 5; i++)
+            if (cudaEventCreate(&ev.e[i]) != cudaSuccess) return nullptr;
+        s->ev_pool.push_back(ev);
+    }
+    return &s->ev_pool[s->ev_used++];
+}
+
+static int launch_force(cf_sim* s) {
+    int n = s->n;
+    const float4* pos = s->pos[s->cur];
+    int kernel = s->opt_force_kernel;
+    if (kernel == 0) kernel = tile_kernel_applicable(s->sc, n, s->ncell) ? 2 : 1;
+    s->last_force_kernel = kernel;
+    if (kernel == 2) {
+        if (int rc = launch_tile_force(s->stream, pos, s->cell_start, s->frc, n, s->ncell, s->sc, s->d_tables,
+                                       &s->launches))
+            return fail(CF_ERR_CUDA, "tile force launch failed: %s", cudaGetErrorString((cudaError_t)rc));
+        return 0;
+    }
+    if (s->sc.uniform_radius)
+        LAUNCH(s, force_pp_kernel<true>, div_up(n, 128), 128, 0, pos, s->cell_start, s->frc, 0, n, s->sc, s->d_tables);
+    else
+        LAUNCH(s, force_pp_kernel<false>, div_up(n, 128), 128, 0, pos, s->cell_start, s->frc, 0, n, s->sc, s->d_tables);
+    return 0;
+}
+
+extern "C" int cf_step(cf_sim* s, const cf_params* p, int n_steps) {
+    ARG(s && n_steps >= 0);
+    if (p) {
+        if (int rc = cf_set_params(s, p)) return rc;
+    }
+    if (int rc = set_device(s)) return rc;
+    if (int rc = prepare_step_const(s)) return rc;
+    if (s->n == 0) return CF_OK;
+    for (int it = 0; it < n_steps; it++) {
+        StepEvents* ev = next_events(s);
+        if (ev) CU(cudaEventRecord(ev->e[0], s->stream));
+        if (int rc = ensure_sorted(s)) return rc;
+        if (ev) CU(cudaEventRecord(ev->e[1], s->stream));
+        if (int rc = launch_force(s)) return rc;
+        if (ev) CU(cudaEventRecord(ev->e[2], s->stream));
+        LAUNCH(s, integrate_kernel, div_up(s->n, 256), 256, 0, s->pos[s->cur], s->vel[s->cur], s->frc, s->n, s->sc);
+        if (ev) CU(cudaEventRecord(ev->e[3], s->stream));
+        s->sorted_valid = false;
+    }
+    CU(cudaGetLastError());
+    return CF_OK;
+}
+
+extern "C" int cf_sync(cf_sim* s) {
+    ARG(s);
+    if (int rc = set_device(s)) return rc;
+    CU(cudaStreamSynchronize(s->stream));
+    return CF_OK;
+}
+
+extern "C" int cf_step_host(cf_sim* s, const cf_params* p, const cf_particle* in, const int32_t* counts_in,
+                            cf_particle* out, int32_t* counts_out, int count) {
+    ARG(s && in && out && count >= 0);
+    if (int rc = upload_impl(s, in, counts_in, nullptr, count)) return rc;
+    if (int rc = cf_step(s, p, 1)) return rc;
+    if (count == 0) return CF_OK;
+    LAUNCH(s, soa_to_aos_kernel, div_up(count, 256), 256, 0, s->pos[s->cur], s->vel[s->cur], s->frc,
+           s->id[s->cur], s->d_aos, s->d_counts, count, 1);
+    CU(cudaMemcpyAsync(out, s->d_aos, sizeof(AosParticle) * (size_t)count, cudaMemcpyDeviceToHost, s->stream));
+    if (counts_out)
+        CU(cudaMemcpyAsync(counts_out, s->d_counts, sizeof(int) * (size_t)count, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    return CF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// proximity graph
+// ---------------------------------------------------------------------------------------------
+extern "C" int cf_build_graph(cf_sim* s, float dist, int max_conn, int* n_edges) {
+    ARG(s && n_edges);
+    *n_edges = 0;
+    ARG(max_conn >= 0);
+    if (int rc = set_device(s)) return rc;
+    int mc = std::min(max_conn, CF_MAX_GRAPH_CONN);
+    if (s->n == 0 || mc == 0 || !(dist > 0.f)) {
+        s->n_edges = 0;
+        return CF_OK;
+    }
+    if (int rc = prepare_step_const(s)) return rc;
+    long long need = (long long)s->n * mc;
+    if (need > s->edge_cap) {
+        CU(cudaStreamSynchronize(s->stream));
+        cudaFree(s->edges);
+        cudaFree(s->edge_slots);
+        s->edges = s->edge_slots = nullptr;
+        CU(cudaMalloc(&s->edges, sizeof(int2) * (size_t)need));
+        CU(cudaMalloc(&s->edge_slots, sizeof(int2) * (size_t)need));
+        s->edge_cap = (int)need;
+    }
+    if (s->opt_timing) CU(cudaEventRecord(s->ev_g0, s->stream));
+    if (int rc = ensure_sorted(s)) return rc;
+    float min_edge = 1e30f;
+    for (int a = 0; a < 3; a++) min_edge = std::min(min_edge, s->sc.W[a] / (float)s->sc.dims[a]);
+    int m = (int)ceil((double)dist * (1.0 + 1e-5) / (double)min_edge);
+    m = std::max(m, 1);
+    CU(cudaMemsetAsync(s->d_edge_count, 0, sizeof(int), s->stream));
+    LAUNCH(s, graph_kernel, div_up(s->n, 128), 128, 0, s->pos[s->cur], s->id[s->cur], s->cell_start, 0, s->n,
+           s->sc, dist * dist, mc, m, s->edges, s->edge_slots, s->edge_cap, s->d_edge_count);
+    if (s->opt_timing) {
+        CU(cudaEventRecord(s->ev_g1, s->stream));
+        s->graph_timed = true;
+    }
+    CU(cudaMemcpyAsync(&s->n_edges, s->d_edge_count, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    CU(cudaGetLastError());
+    *n_edges = s->n_edges;
+    return CF_OK;
+}
+
+extern "C" int cf_download_graph_edges(cf_sim* s, cf_edge* edges, int capacity) {
+    ARG(s && (edges || s->n_edges == 0));
+    ARG(capacity >= s->n_edges);
+    if (int rc = set_device(s)) return rc;
+    if (s->n_edges == 0) return CF_OK;
+    CU(cudaMemcpyAsync(edges, s->edges, sizeof(int2) * (size_t)s->n_edges, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    return CF_OK;
+}
+
+extern "C" int cf_download_graph_vertices(cf_sim* s, const cf_color* colors, int num_colors, float* vertices,
+                                          int capacity_edges) {
+    ARG(s && colors && num_colors >= s->T && (vertices || s->n_edges == 0));
+    ARG(capacity_edges >= s->n_edges);
+    if (int rc = set_device(s)) return rc;
+    if (s->n_edges == 0) return CF_OK;
+    if (!s->sorted_valid) return fail(CF_ERR_STATE, "graph vertices requested after the particles moved");
+    float* d_colors = nullptr;
+    float* d_out = nullptr;
+    CU(cudaMalloc(&d_colors, sizeof(float) * 3 * (size_t)num_colors));
+    if (cudaMalloc(&d_out, sizeof(float) * 12 * (size_t)s->n_edges) != cudaSuccess) {
+        cudaFree(d_colors);
+        return fail(CF_ERR_CUDA, "cudaMalloc vertices");
+    }
+    cudaMemcpyAsync(d_colors, colors, sizeof(float) * 3 * (size_t)num_colors, cudaMemcpyHostToDevice, s->stream);
+    LAUNCH(s, graph_vertices_kernel, div_up(s->n_edges, 256), 256, 0, s->edge_slots, s->n_edges, s->pos[s->cur],
+           d_colors, s->T, d_out);
+    cudaMemcpyAsync(vertices, d_out, sizeof(float) * 12 * (size_t)s->n_edges, cudaMemcpyDeviceToHost, s->stream);
+    cudaError_t e = cudaStreamSynchronize(s->stream);
+    cudaFree(d_colors);
+    cudaFree(d_out);
+    if (e != cudaSuccess) return fail(CF_ERR_CUDA, "graph vertices: %s", cudaGetErrorString(e));
+    return CF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// presets applied to a handle (CellFlowWidget::loadPreset order, CellFlowWidget.cpp:1079-1177)
+// ---------------------------------------------------------------------------------------------
+extern "C" int cf_apply_preset(cf_sim* s, const cf_preset* pr) {
+    ARG(s && pr);
+    if (pr->particleCount > 0 && pr->particleCount != s->n)
+        if (int rc = cf_set_particle_count(s, pr->particleCount)) return rc;
+    int T = pr->params.numParticleTypes;
+    ARG(T >= 1 && T <= CF_MAX_PARTICLE_TYPES);
+    if (T != s->T)
+        if (int rc = cf_set_num_particle_types(s, T)) return rc;
+    s->params = pr->params;
+    s->params.numParticleTypes = T;
+    if (pr->numRadio > 0) cf_set_radio_by_type(s, pr->radioByType, pr->numRadio);
+    if (pr->numRawForce > 0) cf_set_raw_force_table(s, pr->rawForceTable, pr->numRawForce);
+    return cf_update_force_table(s, pr->params.forceRange, pr->params.forceBias, pr->params.forceOffset);
+}
+
+// ---------------------------------------------------------------------------------------------
+// introspection
+// ---------------------------------------------------------------------------------------------
+extern "C" int cf_set_option(cf_sim* s, const char* name, double value) {
+    ARG(s && name);
+    std::string k(name);
+    if (k == "stencil") s->opt_stencil = (int)value;
+    else if (k == "force_kernel") s->opt_force_kernel = (int)value;
+    else if (k == "timing") s->opt_timing = (int)value;
+    else if (k == "max_cells_per_particle") s->opt_max_cells_per_particle = value;
+    else return fail(CF_ERR_ARG, "unknown option '%s'", name);
+    s->sorted_valid = false;
+    return CF_OK;
+}
+
+extern "C" int cf_stats_reset(cf_sim* s) {
+    ARG(s);
+    if (int rc = set_device(s)) return rc;
+    CU(cudaStreamSynchronize(s->stream));
+    s->ev_used = 0;
+    s->ms_sort = s->ms_force = s->ms_integrate = s->ms_total = s->ms_graph = 0;
+    s->stat_steps = 0;
+    s->launches = 0;
+    s->graph_timed = false;
+    return CF_OK;
+}
+
+extern "C" int cf_get_stats(cf_sim* s, cf_stats* st) {
+    ARG(s && st);
+    if (int rc = set_device(s)) return rc;
+    CU(cudaStreamSynchronize(s->stream));
+    for (size_t i = 0; i < s->ev_used; i++) {
+        float a = 0, b = 0, c = 0;
+        StepEvents& ev = s->ev_pool[i];
+        cudaEventElapsedTime(&a, ev.e[0], ev.e[1]);
+        cudaEventElapsedTime(&b, ev.e[1], ev.e[2]);
+        cudaEventElapsedTime(&c, ev.e[2], ev.e[3]);
+        s->ms_sort += a;
+        s->ms_force += b;
+        s->ms_integrate += c;
+        s->ms_total += a + b + c;
+        s->stat_steps++;
+    }
+    s->ev_used = 0;
+    if (s->graph_timed) {
+        float g = 0;
+        cudaEventElapsedTime(&g, s->ev_g0, s->ev_g1);
+        s->ms_graph = g;
+        s->graph_timed = false;
+    }
+    memset(st, 0, sizeof(*st));
+    st->ms_total = s->ms_total;
+    st->ms_sort = s->ms_sort;
+    st->ms_force = s->ms_force;
+    st->ms_integrate = s->ms_integrate;
+    st->ms_graph = s->ms_graph;
+    st->steps = s->stat_steps;
+    st->launches = s->launches;
+    for (int a = 0; a < 3; a++) st->grid[a] = s->sc.dims[a];
+    st->stencil = 1;
+    st->n_owned = s->n;
+    st->n_ghost = 0;
+    if (s->n > 0) {
+        unsigned long long acc = 0;
+        CU(cudaMemsetAsync(s->d_accum, 0, sizeof(unsigned long long), s->stream));
+        sum_counts_kernel<<<148 * 4, 256, 0, s->stream>>>(s->frc, s->n, s->d_accum);
+        CU(cudaMemcpyAsync(&acc, s->d_accum, sizeof(acc), cudaMemcpyDeviceToHost, s->stream));
+        CU(cudaStreamSynchronize(s->stream));
+        st->accepted_pairs = (long long)acc;
+        if (s->sorted_valid || s->cell_start) {
+            // tests executed by the stencil of the last force pass: sum over cells of
+            // n_cell * (particles in its neighbour cells); valid while cell_start is current
+            CU(cudaMemsetAsync(s->d_accum, 0, sizeof(unsigned long long), s->stream));
+            count_tests_kernel<<<div_up(s->ncell, 128), 128, 0, s->stream>>>(s->cell_start, s->ncell, s->sc, s->d_accum);
+            CU(cudaMemcpyAsync(&acc, s->d_accum, sizeof(acc), cudaMemcpyDeviceToHost, s->stream));
+            CU(cudaStreamSynchronize(s->stream));
+            st->tested_pairs = (long long)acc;
+        }
+    }
+    return CF_OK;
+}
+
+extern "C" int cf_download_cell_keys(cf_sim* s, uint32_t* keys, int32_t* ids, int capacity, int* count) {
+    ARG(s && count);
+    *count = s->n;
+    ARG(capacity >= s->n);
+    if (int rc = set_device(s)) return rc;
+    if (int rc = prepare_step_const(s)) return rc;
+    if (s->n == 0) return CF_OK;
+    if (int rc = ensure_sorted(s)) return rc;
+    if (keys) CU(cudaMemcpyAsync(keys, s->keys[0], sizeof(uint32_t) * (size_t)s->n, cudaMemcpyDeviceToHost, s->stream));
+    if (ids) CU(cudaMemcpyAsync(ids, s->id[s->cur], sizeof(int) * (size_t)s->n, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    return CF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// multi-GPU slabs: implemented in comm.cu
+// ---------------------------------------------------------------------------------------------
