@@ -106,7 +106,16 @@ def test_f64_error_budget():
     F, X, fa = O.step_f64(state, counts, p, table, radio, 4)
     err = np.abs(out["acc"] - F).max(1) / (fa + 1e-30)
     assert cnt.mean() > 30
-    assert err.max() < 2e-6
+    assert err.max() < 1e-6
+    # sparse neighbourhoods (struct defaults, ~0.8 neighbours): still fine under the gross norm,
+    # while relative to the NET pair force the reference's own fp32 arithmetic exceeds 1e-5
+    p2 = O.Params()
+    raw, radio2 = O.default_tables(6)
+    eff = O.force_table(raw, 6, 0.28, -0.20, 1.0)
+    s2, c2 = U.random_state(20000, 6, 5, p2.canvas, "cube")
+    o2, n2, g2 = O.step(s2, c2, p2, eff, radio2, "cells", 4)
+    F2, _, ga2 = O.step_f64(s2, c2, p2, eff, radio2, 4)
+    assert (np.abs(o2["acc"] - F2).max(1) / (ga2 + 1e-30)).max() < 1e-6
     d = U.wrapped_abs_diff(out["pos"], np.mod(X, p.canvas), p.canvas)
     assert d.max() < 2e-3  # ulp(pos + W) = 9.8e-4 at W = 8000
 

@@ -81,9 +81,11 @@ def random_state(n, T, seed, canvas, mode="uniform", vel_scale=5.0, cube=2000.0)
 
 
 def force_rel_err(acc, acc_ref, fabs, mult):
-    """max_i |acc_i - ref_i|_inf / (mult_i * sum_j |s_ij|) — the north_star's 1e-5 norm, taken
-    against the summed magnitude of the pair terms (a net force of near-cancelling terms has no
-    meaningful relative error of its own; SURVEY.md section 7 'parity norm')."""
+    """max_i |acc_i - ref_i|_inf / (mult_i * sum_j |fv_ij| (|rep e_ij| + |att r_ij|)) — the
+    north_star's 1e-5 norm, taken against the summed magnitude of the pair terms.  A net force of
+    near-cancelling terms has no meaningful relative error of its own (SURVEY.md section 7 'parity
+    norm'): the law's repulsion and attraction terms cancel at a radius inside the cutoff, and a
+    particle whose only neighbour sits there has |net| ~ 1e-3 of either term."""
     scale = np.abs(mult) * fabs.astype(np.float64) + 1e-30
     err = np.abs(acc.astype(np.float64) - acc_ref.astype(np.float64)).max(axis=1)
     return err / scale
