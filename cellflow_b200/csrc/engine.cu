@@ -69,6 +69,7 @@ struct cf_sim {
     float raw[CF_TT_MAX];
     float radio[CF_T_MAX];
     float force[CF_TT_MAX];
+    float half_host[CF_T_MAX];
     bool force_overridden = false;
 
     float4* pos[2] = {nullptr, nullptr};
@@ -96,6 +97,14 @@ struct cf_sim {
     AosParticle* d_aos = nullptr;
     int* d_counts = nullptr;
     unsigned long long* d_accum = nullptr;
+
+    // tile kernel
+    int2* d_tiles = nullptr;
+    size_t tiles_cap = 0;
+    int* d_tile_ctrl = nullptr;
+    float* d_half = nullptr;      // per-type conservative half radius (non-uniform radii)
+    bool half_bound_ok = true;
+    int sm_count = 148;
 
     // options
     int opt_stencil = 0;     // reserved (0 = automatic)
@@ -280,6 +289,19 @@ static float compute_tables(cf_sim* s, DeviceTables& t, bool& uniform) {
     uniform = true;
     for (int i = 1; i < T * T; i++)
         if (t.cut2[i] != t.cut2[0] || t.inv_reff[i] != t.inv_reff[0]) uniform = false;
+    // conservative per-type half radii for the tile kernel's prefilter:
+    // (h_a + h_b)^2 evaluated in fp32 must not fall below cut2[a][b]
+    s->half_bound_ok = true;
+    for (int a = 0; a < T; a++) {
+        double at = (double)fmaf(s->radio[a], s->params.ratioWithLFO, 1.0f);
+        s->half_host[a] = (float)(0.5 * (double)s->params.radius * at * (1.0 + 4e-6));
+    }
+    for (int a = 0; a < T; a++)
+        for (int b = 0; b < T; b++) {
+            volatile float h = s->half_host[a] + s->half_host[b];
+            volatile float h2 = h * h;
+            if (t.cut2[a * T + b] > 0.f && !(h2 >= t.cut2[a * T + b] && h > 0.f)) s->half_bound_ok = false;
+        }
     return rmax;
 }
 
@@ -299,7 +321,7 @@ static int prepare_step_const(cf_sim* s) {
     // the grid has at most opt_max_cells_per_particle * n cells
     double vol = (double)W[0] * W[1] * W[2];
     double max_cells = std::max(64.0, s->opt_max_cells_per_particle * (double)std::max(s->n, 1));
-    max_cells = std::min(max_cells, 16777216.0);
+    max_cells = std::min(max_cells, 16777216.0); // cell * T + type must fit the 32-bit sort key
     double edge = std::max((double)rmax * (1.0 + 1e-5), cbrt(vol / max_cells));
     if (!(edge > 0.0)) edge = cbrt(vol / max_cells);
     long long ncell = 1;
@@ -338,6 +360,7 @@ static int prepare_step_const(cf_sim* s) {
         CU(cudaMalloc(&s->cell_start, s->cell_cap * sizeof(int)));
     }
     CU(cudaMemcpyAsync(s->d_tables, &t, sizeof(t), cudaMemcpyHostToDevice, s->stream));
+    CU(cudaMemcpyAsync(s->d_half, s->half_host, sizeof(float) * CF_T_MAX, cudaMemcpyHostToDevice, s->stream));
     // pageable source: the copy is staged before the call returns, `t` may go out of scope
     return 0;
 }
@@ -353,7 +376,7 @@ static int ensure_sorted(cf_sim* s) {
     int blocks = div_up(n, 256);
     LAUNCH(s, cell_key_kernel, blocks, 256, 0, s->pos[cur], s->keys[0], s->vals[0], n, s->sc);
     int bits = 1;
-    while ((1ll << bits) < (long long)s->ncell) bits++;
+    while ((1ll << bits) < (long long)s->ncell * s->T) bits++;
     int passes = div_up(bits, 8);
     int bits_per_pass = div_up(bits, passes);
     int items = 4096;
@@ -379,7 +402,7 @@ static int ensure_sorted(cf_sim* s) {
     LAUNCH(s, reorder_kernel, blocks, 256, 0, s->vals[src], s->pos[cur], s->vel[cur], s->id[cur],
            s->pos[nxt], s->vel[nxt], s->id[nxt], n);
     LAUNCH(s, cell_bounds_kernel, div_up(s->ncell + 1, 256), 256, 0, s->keys[src], n, s->cell_start,
-           s->ncell, 0);
+           s->ncell, 0, s->T);
     if (src != 0) std::swap(s->keys[0], s->keys[1]), std::swap(s->vals[0], s->vals[1]);
     // keys[0] now holds the sorted keys of the current order
     s->cur = nxt;
@@ -446,6 +469,12 @@ extern "C" int cf_create(int particle_count, int num_types, int device, cf_sim**
     int rc = alloc_particle_buffers(s, particle_count);
     if (rc == 0 && cudaMalloc(&s->d_tables, sizeof(DeviceTables)) != cudaSuccess) rc = fail(CF_ERR_CUDA, "cudaMalloc tables");
     if (rc == 0 && cudaMalloc(&s->d_edge_count, sizeof(int)) != cudaSuccess) rc = fail(CF_ERR_CUDA, "cudaMalloc");
+    if (rc == 0 && cudaMalloc(&s->d_tile_ctrl, 2 * sizeof(int)) != cudaSuccess) rc = fail(CF_ERR_CUDA, "cudaMalloc");
+    if (rc == 0 && cudaMalloc(&s->d_half, CF_T_MAX * sizeof(float)) != cudaSuccess) rc = fail(CF_ERR_CUDA, "cudaMalloc");
+    if (rc == 0) {
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) s->sm_count = prop.multiProcessorCount;
+    }
     if (rc == 0 && cudaMalloc(&s->d_accum, sizeof(unsigned long long)) != cudaSuccess) rc = fail(CF_ERR_CUDA, "cudaMalloc");
     if (rc == 0 && cudaEventCreate(&s->ev_g0) != cudaSuccess) rc = fail(CF_ERR_CUDA, "cudaEventCreate");
     if (rc == 0 && cudaEventCreate(&s->ev_g1) != cudaSuccess) rc = fail(CF_ERR_CUDA, "cudaEventCreate");
@@ -469,6 +498,9 @@ extern "C" int cf_destroy(cf_sim* s) {
     cudaFree(s->d_tables);
     cudaFree(s->d_edge_count);
     cudaFree(s->d_accum);
+    cudaFree(s->d_tiles);
+    cudaFree(s->d_tile_ctrl);
+    cudaFree(s->d_half);
     for (auto& ev : s->ev_pool)
         for (int i = 0; i < 5; i++) cudaEventDestroy(ev.e[i]);
     if (s->ev_g0) cudaEventDestroy(s->ev_g0);
@@ -716,12 +748,31 @@ static int launch_force(cf_sim* s) {
     int n = s->n;
     const float4* pos = s->pos[s->cur];
     int kernel = s->opt_force_kernel;
-    if (kernel == 0) kernel = tile_kernel_applicable(s->sc, n, s->ncell) ? 2 : 1;
+    bool tile_ok = tile_kernel_applicable(s->sc, n, s->ncell) && (s->sc.uniform_radius || s->half_bound_ok);
+    if (kernel == 0) kernel = tile_ok ? 2 : 1;
+    if (kernel == 2 && !(s->sc.dims[1] >= 4 && s->sc.dims[2] >= 4 && (!s->sc.periodic_x || s->sc.dims[0] >= 4) &&
+                         (s->sc.uniform_radius || s->half_bound_ok)))
+        kernel = 1; // the tile kernel's per-run wrap needs >= 4 cells per periodic axis
     s->last_force_kernel = kernel;
     if (kernel == 2) {
-        if (int rc = launch_tile_force(s->stream, pos, s->cell_start, s->frc, n, s->ncell, s->sc, s->d_tables,
-                                       &s->launches))
-            return fail(CF_ERR_CUDA, "tile force launch failed: %s", cudaGetErrorString((cudaError_t)rc));
+        size_t need = (size_t)s->ncell + (size_t)n / TK_TI + 2;
+        if (need > s->tiles_cap) {
+            CU(cudaStreamSynchronize(s->stream));
+            cudaFree(s->d_tiles);
+            s->d_tiles = nullptr;
+            s->tiles_cap = need + need / 4;
+            CU(cudaMalloc(&s->d_tiles, s->tiles_cap * sizeof(int2)));
+        }
+        CU(cudaMemsetAsync(s->d_tile_ctrl, 0, 2 * sizeof(int), s->stream));
+        LAUNCH(s, build_tiles_kernel, div_up(s->ncell, 256), 256, 0, s->cell_start, s->ncell, 0, s->sc.dims[0] - 1,
+               s->sc.dims[1] * s->sc.dims[2], s->d_tiles, s->d_tile_ctrl);
+        int grid = s->sm_count * 4;
+        if (s->sc.uniform_radius)
+            LAUNCH(s, force_tile_kernel<true>, grid, TK_THREADS, 0, pos, s->cell_start, s->d_tiles, s->d_tile_ctrl,
+                   s->frc, s->sc, s->d_tables, 0.f, s->d_half);
+        else
+            LAUNCH(s, force_tile_kernel<false>, grid, TK_THREADS, 0, pos, s->cell_start, s->d_tiles, s->d_tile_ctrl,
+                   s->frc, s->sc, s->d_tables, 0.f, s->d_half);
         return 0;
     }
     if (s->sc.uniform_radius)

@@ -67,7 +67,7 @@ CASES = [
 
 
 @pytest.mark.parametrize("name,n,mode,over,radio", CASES)
-@pytest.mark.parametrize("kernel", [1])
+@pytest.mark.parametrize("kernel", [1, 2])
 def test_step_parity(name, n, mode, over, radio, kernel):
     p, table, r0 = U.config(name, **over)
     radio = np.float32(radio) if radio is not None else r0
@@ -156,12 +156,13 @@ def test_cell_assignment_bit_exact():
     sim = make_sim(p, table, radio, state, counts)
     keys, ids = sim.cellKeys()
     dims = np.int32(list(sim.stats().grid))
-    want = O.cell_keys(state, p.canvas, dims)
+    T = p.numParticleTypes
+    want = O.cell_keys(state, p.canvas, dims) * np.uint32(T) + state["ptype"]   # key = cell*T + type
     assert sorted(ids.tolist()) == list(range(len(state)))          # a permutation
     assert np.array_equal(keys, want[ids])                          # key of every slot
     assert np.all(np.diff(keys.astype(np.int64)) >= 0)              # sorted
     same = keys[1:] == keys[:-1]
-    assert np.all(ids[1:][same] > ids[:-1][same])                   # stable inside a cell
+    assert np.all(ids[1:][same] > ids[:-1][same])                   # stable inside a (cell, type)
     sim.close()
 
 
