@@ -21,6 +21,13 @@ struct StepConst {
     float inv[3];    // (float)dims / W      — cell index = min((int)(pos * inv), dims - 1)
     int dims[3];     // cells per axis; linear cell = (cx * dims[1] + cy) * dims[2] + cz
     int periodic_x;  // 0 when x is slab-decomposed (ghost layers replace the wrap)
+    // x cell coordinate = clamp((int)((x - x_org) * inv[0]), 0, x_cells - 1) + x_off.  Single GPU:
+    // x_org = 0, x_off = 0, x_cells = dims[0].  Slab mode: x_org = slab lower bound, x_off = 1
+    // (layer 0 and layer dims[0]-1 are ghost layers), x_cells = owned layers.
+    float x_org;
+    int x_off, x_cells;
+    float gshift_lo, gshift_hi; // minimum-image shift of the two ghost layers (+-W at the seam)
+    int gx_lo, gx_hi;           // x layers the (non-periodic) proximity graph may look at
     int T;
     float repulsion, attraction;
     float nk_log2e;  // -k * log2(e): exp(-k r^2) = exp2(nk_log2e * r^2)
@@ -46,8 +53,14 @@ __device__ __forceinline__ int cf_cell_coord(float x, float inv, int n) {
     return c < 0 ? 0 : c;
 }
 
+__device__ __forceinline__ int cf_cell_coord_x(float x, const StepConst& c) {
+    int v = (int)__fmul_rn(__fsub_rn(x, c.x_org), c.inv[0]);
+    v = v > c.x_cells - 1 ? c.x_cells - 1 : v;
+    return (v < 0 ? 0 : v) + c.x_off;
+}
+
 __device__ __forceinline__ uint32_t cf_cell_key(float4 p, const StepConst& c) {
-    int cx = cf_cell_coord(p.x, c.inv[0], c.dims[0]);
+    int cx = cf_cell_coord_x(p.x, c);
     int cy = cf_cell_coord(p.y, c.inv[1], c.dims[1]);
     int cz = cf_cell_coord(p.z, c.inv[2], c.dims[2]);
     return (uint32_t)((cx * c.dims[1] + cy) * c.dims[2] + cz);

@@ -20,9 +20,11 @@
 #include "cf_device.cuh"
 #include "kernels_force.cuh"
 #include "kernels_graph.cuh"
+#include "kernels_slab.cuh"
 #include "kernels_sort.cuh"
 #include "kernels_state.cuh"
 #include "kernels_tile.cuh"
+#include "nccl_dyn.h"
 
 static_assert(sizeof(AosParticle) == 44 && sizeof(cf_particle) == 44, "reference Particle is 44 B");
 
@@ -56,7 +58,7 @@ extern "C" const char* cf_version(void) { return "cellflow_b200 0.1 (sm_100a)"; 
 // handle
 // ---------------------------------------------------------------------------------------------
 struct StepEvents {
-    cudaEvent_t e[5]; // begin, after sort, after force, after integrate, (spare)
+    cudaEvent_t e[6]; // begin, after cell list, after force, after integrate, exchange begin/end
 };
 
 struct cf_sim {
@@ -106,6 +108,27 @@ struct cf_sim {
     bool half_bound_ok = true;
     int sm_count = 148;
 
+    // slab decomposition (multi-GPU); single GPU: base = 0, slab = false
+    int base = 0;            // first owned slot
+    bool slab = false;
+    int rank = 0, world = 1;
+    ncclComm_t comm = nullptr;
+    int cap_own = 0, cap_halo = 0, cap_mig = 0;
+    int nxl = 0;             // owned x layers
+    SlabGeom geom;
+    char* send_mig[2] = {nullptr, nullptr};  // [0] to/from left, [1] to/from right
+    char* recv_mig[2] = {nullptr, nullptr};
+    char* send_halo[2] = {nullptr, nullptr};
+    char* recv_halo[2] = {nullptr, nullptr};
+    uint32_t* akeys[2] = {nullptr, nullptr};
+    uint32_t* avals[2] = {nullptr, nullptr};
+    uint32_t* gkeys[2] = {nullptr, nullptr};
+    int* d_slab_counts = nullptr;  // [0..2] class counts, [3] error flag, [4..5] ghost counts
+    int* h_slab_counts = nullptr;  // pinned mirror
+    int n_ghost[2] = {0, 0};
+    long long n_total = 0;         // global particle count (slab mode)
+    double ms_exchange = 0;
+
     // options
     int opt_stencil = 0;     // reserved (0 = automatic)
     int opt_force_kernel = 0; // 0 auto, 1 per-particle, 2 tile
@@ -131,6 +154,13 @@ struct cf_sim {
     } while (0)
 
 static inline int div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// Owned particles occupy slots [base, base + n) of the state arrays (base = 0 on a single GPU;
+// in slab mode the slots before/after hold the ghost layers).
+static inline float4* opos(cf_sim* s) { return s->pos[s->cur] + s->base; }
+static inline float4* ovel(cf_sim* s) { return s->vel[s->cur] + s->base; }
+static inline int* oid(cf_sim* s) { return s->id[s->cur] + s->base; }
+static inline float4* ofrc(cf_sim* s) { return s->frc + s->base; }
 
 static int set_device(const cf_sim* sim) {
     CU(cudaSetDevice(sim->device));
@@ -305,6 +335,8 @@ static float compute_tables(cf_sim* s, DeviceTables& t, bool& uniform) {
     return rmax;
 }
 
+static float slab_bound(const cf_sim* s, int r);
+
 // Chooses the cell grid for the current parameters and uploads the tables.
 static int prepare_step_const(cf_sim* s) {
     const cf_params& p = s->params;
@@ -319,7 +351,7 @@ static int prepare_step_const(cf_sim* s) {
     float W[3] = {p.canvasWidth, p.canvasHeight, p.canvasDepth};
     // cell edge >= R_max (1e-5 margin covers the rounding of pos * inv), and coarse enough that
     // the grid has at most opt_max_cells_per_particle * n cells
-    double vol = (double)W[0] * W[1] * W[2];
+    double vol = (double)W[0] * W[1] * W[2] / (s->slab ? s->world : 1);
     double max_cells = std::max(64.0, s->opt_max_cells_per_particle * (double)std::max(s->n, 1));
     max_cells = std::min(max_cells, 16777216.0); // cell * T + type must fit the 32-bit sort key
     double edge = std::max((double)rmax * (1.0 + 1e-5), cbrt(vol / max_cells));
@@ -336,6 +368,36 @@ static int prepare_step_const(cf_sim* s) {
         ncell *= d;
     }
     c.periodic_x = 1;
+    c.x_org = 0.f;
+    c.x_off = 0;
+    c.x_cells = c.dims[0];
+    c.gshift_lo = c.gshift_hi = 0.f;
+    c.gx_lo = 0;
+    c.gx_hi = c.dims[0] - 1;
+    if (s->slab) {
+        // owned x layers over the slab, one ghost layer on each side
+        s->geom.x_lo = slab_bound(s, s->rank);
+        s->geom.x_hi = slab_bound(s, s->rank + 1);
+        s->geom.W = W[0];
+        s->geom.slab_w = W[0] / (float)s->world;
+        double slab_w = (double)W[0] / s->world;
+        ncell /= c.dims[0];
+        int nxl = std::max(1, std::min((int)floor(slab_w / edge), 1022));
+        s->nxl = nxl;
+        c.dims[0] = nxl + 2;
+        c.inv[0] = (float)nxl / (s->geom.x_hi - s->geom.x_lo);
+        c.periodic_x = 0;
+        c.x_org = s->geom.x_lo;
+        c.x_off = 1;
+        c.x_cells = nxl;
+        c.gshift_lo = s->rank == 0 ? -W[0] : 0.f;
+        c.gshift_hi = s->rank == s->world - 1 ? W[0] : 0.f;
+        c.gx_lo = s->rank == 0 ? 1 : 0;
+        c.gx_hi = s->rank == s->world - 1 ? nxl : nxl + 1;
+        ncell *= c.dims[0];
+        if ((double)rmax * (1.0 + 1e-5) > slab_w)
+            return fail(CF_ERR_ARG, "interaction radius %.1f exceeds the slab width %.1f: use fewer GPUs", rmax, slab_w);
+    }
     c.T = s->T;
     c.repulsion = p.repulsion;
     c.attraction = p.attraction;
@@ -409,6 +471,12 @@ static int ensure_sorted(cf_sim* s) {
     s->sorted_valid = true;
     CU(cudaGetLastError());
     return 0;
+}
+
+#include "slab_host.inl"
+
+static int build_cell_list(cf_sim* s, cudaEvent_t ev_x0 = nullptr, cudaEvent_t ev_x1 = nullptr) {
+    return s->slab ? ensure_sorted_slab(s, ev_x0, ev_x1) : ensure_sorted(s);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -492,6 +560,7 @@ extern "C" int cf_destroy(cf_sim* s) {
     if (!s) return CF_OK;
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
+    slab_free(s);
     free_particle_buffers(s);
     cudaFree(s->hist);
     cudaFree(s->cell_start);
@@ -502,7 +571,7 @@ extern "C" int cf_destroy(cf_sim* s) {
     cudaFree(s->d_tile_ctrl);
     cudaFree(s->d_half);
     for (auto& ev : s->ev_pool)
-        for (int i = 0; i < 5; i++) cudaEventDestroy(ev.e[i]);
+        for (int i = 0; i < 6; i++) cudaEventDestroy(ev.e[i]);
     if (s->ev_g0) cudaEventDestroy(s->ev_g0);
     if (s->ev_g1) cudaEventDestroy(s->ev_g1);
     if (s->stream) cudaStreamDestroy(s->stream);
@@ -603,19 +672,41 @@ extern "C" int cf_rotate_radio_by_type(cf_sim* s) { // .cu:594-600
 extern "C" int cf_init_particles(cf_sim* s, uint64_t seed, int mode) {
     ARG(s && (mode == CF_INIT_SPAWN_CUBE || mode == CF_INIT_UNIFORM));
     if (int rc = set_device(s)) return rc;
+    if (s->slab) return slab_init_particles(s, s->n_total, seed, mode);
     if (s->n > 0)
-        LAUNCH(s, init_particles_kernel, div_up(s->n, 256), 256, 0, s->pos[s->cur], s->vel[s->cur], s->frc,
-               s->id[s->cur], s->n, 0, s->T, seed, mode, s->params.canvasWidth, s->params.canvasHeight,
+        LAUNCH(s, init_particles_kernel, div_up(s->n, 256), 256, 0, opos(s), ovel(s), ofrc(s),
+               oid(s), s->n, 0, s->T, seed, mode, s->params.canvasWidth, s->params.canvasHeight,
                s->params.canvasDepth);
     s->sorted_valid = false;
     CU(cudaGetLastError());
     return CF_OK;
 }
 
+extern "C" int cf_init_particles_global(cf_sim* s, int64_t n_total, uint64_t seed, int mode) {
+    ARG(s && (mode == CF_INIT_SPAWN_CUBE || mode == CF_INIT_UNIFORM));
+    if (!s->slab) return fail(CF_ERR_STATE, "cf_init_particles_global needs cf_comm_init first");
+    if (int rc = set_device(s)) return rc;
+    return slab_init_particles(s, n_total, seed, mode);
+}
+
+extern "C" int cf_slab_bounds(cf_sim* s, float* lo, float* hi) {
+    ARG(s && lo && hi);
+    if (!s->slab) {
+        *lo = 0.f;
+        *hi = s->params.canvasWidth;
+        return CF_OK;
+    }
+    *lo = slab_bound(s, s->rank);
+    *hi = slab_bound(s, s->rank + 1);
+    return CF_OK;
+}
+
 static int upload_impl(cf_sim* s, const cf_particle* aos, const int32_t* counts, const int32_t* ids,
                        int count) {
     if (int rc = set_device(s)) return rc;
-    if (count > s->cap) {
+    if (s->slab) {
+        if (count > s->cap_own) return fail(CF_ERR_CAPACITY, "%d particles exceed the rank capacity %d", count, s->cap_own);
+    } else if (count > s->cap) {
         CU(cudaStreamSynchronize(s->stream));
         if (int rc = alloc_particle_buffers(s, count)) return rc;
     }
@@ -630,7 +721,7 @@ static int upload_impl(cf_sim* s, const cf_particle* aos, const int32_t* counts,
         CU(cudaMemcpyAsync(d_ids, ids, sizeof(int) * (size_t)count, cudaMemcpyHostToDevice, s->stream));
     }
     LAUNCH(s, aos_to_soa_kernel, div_up(count, 256), 256, 0, s->d_aos, counts ? s->d_counts : nullptr, d_ids,
-           s->pos[s->cur], s->vel[s->cur], s->frc, s->id[s->cur], count);
+           opos(s), ovel(s), ofrc(s), oid(s), count);
     s->sorted_valid = false;
     CU(cudaGetLastError());
     return CF_OK;
@@ -652,8 +743,8 @@ extern "C" int cf_download_particles(cf_sim* s, cf_particle* aos, int count) {
     ARG(s && aos && count == s->n);
     if (int rc = set_device(s)) return rc;
     if (count == 0) return CF_OK;
-    LAUNCH(s, soa_to_aos_kernel, div_up(count, 256), 256, 0, s->pos[s->cur], s->vel[s->cur], s->frc,
-           s->id[s->cur], s->d_aos, s->d_counts, count, 1);
+    LAUNCH(s, soa_to_aos_kernel, div_up(count, 256), 256, 0, opos(s), ovel(s), ofrc(s),
+           oid(s), s->d_aos, s->d_counts, count, 1);
     CU(cudaMemcpyAsync(aos, s->d_aos, sizeof(AosParticle) * (size_t)count, cudaMemcpyDeviceToHost, s->stream));
     CU(cudaStreamSynchronize(s->stream));
     return CF_OK;
@@ -666,11 +757,11 @@ extern "C" int cf_download_particles_ids(cf_sim* s, cf_particle* aos, int32_t* c
     ARG(capacity >= s->n);
     if (int rc = set_device(s)) return rc;
     if (s->n == 0) return CF_OK;
-    LAUNCH(s, soa_to_aos_kernel, div_up(s->n, 256), 256, 0, s->pos[s->cur], s->vel[s->cur], s->frc,
-           s->id[s->cur], s->d_aos, s->d_counts, s->n, 0);
+    LAUNCH(s, soa_to_aos_kernel, div_up(s->n, 256), 256, 0, opos(s), ovel(s), ofrc(s),
+           oid(s), s->d_aos, s->d_counts, s->n, 0);
     if (aos) CU(cudaMemcpyAsync(aos, s->d_aos, sizeof(AosParticle) * (size_t)s->n, cudaMemcpyDeviceToHost, s->stream));
     if (counts) CU(cudaMemcpyAsync(counts, s->d_counts, sizeof(int) * (size_t)s->n, cudaMemcpyDeviceToHost, s->stream));
-    if (ids) CU(cudaMemcpyAsync(ids, s->id[s->cur], sizeof(int) * (size_t)s->n, cudaMemcpyDeviceToHost, s->stream));
+    if (ids) CU(cudaMemcpyAsync(ids, oid(s), sizeof(int) * (size_t)s->n, cudaMemcpyDeviceToHost, s->stream));
     CU(cudaStreamSynchronize(s->stream));
     return CF_OK;
 }
@@ -680,7 +771,7 @@ extern "C" int cf_upload_neighbor_counts(cf_sim* s, const int32_t* counts, int c
     if (int rc = set_device(s)) return rc;
     if (count == 0) return CF_OK;
     CU(cudaMemcpyAsync(s->d_counts, counts, sizeof(int) * (size_t)count, cudaMemcpyHostToDevice, s->stream));
-    LAUNCH(s, scatter_counts_kernel, div_up(count, 256), 256, 0, s->d_counts, s->id[s->cur], s->vel[s->cur], count);
+    LAUNCH(s, scatter_counts_kernel, div_up(count, 256), 256, 0, s->d_counts, oid(s), ovel(s), count);
     CU(cudaGetLastError());
     return CF_OK;
 }
@@ -689,8 +780,8 @@ extern "C" int cf_download_neighbor_counts(cf_sim* s, int32_t* counts, int count
     ARG(s && counts && count == s->n);
     if (int rc = set_device(s)) return rc;
     if (count == 0) return CF_OK;
-    LAUNCH(s, soa_to_aos_kernel, div_up(count, 256), 256, 0, s->pos[s->cur], s->vel[s->cur], s->frc,
-           s->id[s->cur], s->d_aos, s->d_counts, count, 1);
+    LAUNCH(s, soa_to_aos_kernel, div_up(count, 256), 256, 0, opos(s), ovel(s), ofrc(s),
+           oid(s), s->d_aos, s->d_counts, count, 1);
     CU(cudaMemcpyAsync(counts, s->d_counts, sizeof(int) * (size_t)count, cudaMemcpyDeviceToHost, s->stream));
     CU(cudaStreamSynchronize(s->stream));
     return CF_OK;
@@ -701,7 +792,7 @@ extern "C" int cf_move_universe(cf_sim* s, float dx, float dy, float dz) {
     if (int rc = set_device(s)) return rc;
     if (s->n == 0) return CF_OK;
     // the reference passes the DEFAULT canvas here (.cu:586-589); the engine uses the live one
-    LAUNCH(s, move_universe_kernel, div_up(s->n, 256), 256, 0, s->pos[s->cur], s->n, dx, dy, dz,
+    LAUNCH(s, move_universe_kernel, div_up(s->n, 256), 256, 0, opos(s), s->n, dx, dy, dz,
            s->params.canvasWidth, s->params.canvasHeight, s->params.canvasDepth);
     s->sorted_valid = false;
     CU(cudaGetLastError());
@@ -737,7 +828,7 @@ static StepEvents* next_events(cf_sim* s) {
     if (s->ev_used == s->ev_pool.size()) {
         if (s->ev_pool.size() >= 4096) return nullptr;
         StepEvents ev;
-        for (int i = 0; i < 5; i++)
+        for (int i = 0; i < 6; i++)
             if (cudaEventCreate(&ev.e[i]) != cudaSuccess) return nullptr;
         s->ev_pool.push_back(ev);
     }
@@ -748,11 +839,12 @@ static int launch_force(cf_sim* s) {
     int n = s->n;
     const float4* pos = s->pos[s->cur];
     int kernel = s->opt_force_kernel;
-    bool tile_ok = tile_kernel_applicable(s->sc, n, s->ncell) && (s->sc.uniform_radius || s->half_bound_ok);
+    const int global_nx = s->slab ? s->nxl * s->world : s->sc.dims[0];
+    const bool wrap_ok = s->sc.dims[1] >= 4 && s->sc.dims[2] >= 4 && global_nx >= 4 &&
+                         (s->sc.uniform_radius || s->half_bound_ok);
+    bool tile_ok = wrap_ok && tile_kernel_applicable(s->sc, n, s->ncell);
     if (kernel == 0) kernel = tile_ok ? 2 : 1;
-    if (kernel == 2 && !(s->sc.dims[1] >= 4 && s->sc.dims[2] >= 4 && (!s->sc.periodic_x || s->sc.dims[0] >= 4) &&
-                         (s->sc.uniform_radius || s->half_bound_ok)))
-        kernel = 1; // the tile kernel's per-run wrap needs >= 4 cells per periodic axis
+    if (kernel == 2 && !wrap_ok) kernel = 1; // the tile kernel's per-run wrap needs >= 4 cells per periodic axis
     s->last_force_kernel = kernel;
     if (kernel == 2) {
         size_t need = (size_t)s->ncell + (size_t)n / TK_TI + 2;
@@ -764,7 +856,8 @@ static int launch_force(cf_sim* s) {
             CU(cudaMalloc(&s->d_tiles, s->tiles_cap * sizeof(int2)));
         }
         CU(cudaMemsetAsync(s->d_tile_ctrl, 0, 2 * sizeof(int), s->stream));
-        LAUNCH(s, build_tiles_kernel, div_up(s->ncell, 256), 256, 0, s->cell_start, s->ncell, 0, s->sc.dims[0] - 1,
+        LAUNCH(s, build_tiles_kernel, div_up(s->ncell, 256), 256, 0, s->cell_start, s->ncell, s->sc.x_off,
+               s->sc.x_off + s->sc.x_cells - 1,
                s->sc.dims[1] * s->sc.dims[2], s->d_tiles, s->d_tile_ctrl);
         int grid = s->sm_count * 4;
         if (s->sc.uniform_radius)
@@ -776,9 +869,9 @@ static int launch_force(cf_sim* s) {
         return 0;
     }
     if (s->sc.uniform_radius)
-        LAUNCH(s, force_pp_kernel<true>, div_up(n, 128), 128, 0, pos, s->cell_start, s->frc, 0, n, s->sc, s->d_tables);
+        LAUNCH(s, force_pp_kernel<true>, div_up(n, 128), 128, 0, pos, s->cell_start, s->frc, s->base, n, s->sc, s->d_tables);
     else
-        LAUNCH(s, force_pp_kernel<false>, div_up(n, 128), 128, 0, pos, s->cell_start, s->frc, 0, n, s->sc, s->d_tables);
+        LAUNCH(s, force_pp_kernel<false>, div_up(n, 128), 128, 0, pos, s->cell_start, s->frc, s->base, n, s->sc, s->d_tables);
     return 0;
 }
 
@@ -789,15 +882,16 @@ extern "C" int cf_step(cf_sim* s, const cf_params* p, int n_steps) {
     }
     if (int rc = set_device(s)) return rc;
     if (int rc = prepare_step_const(s)) return rc;
-    if (s->n == 0) return CF_OK;
+    if (s->n == 0 && !s->slab) return CF_OK;
     for (int it = 0; it < n_steps; it++) {
         StepEvents* ev = next_events(s);
         if (ev) CU(cudaEventRecord(ev->e[0], s->stream));
-        if (int rc = ensure_sorted(s)) return rc;
+        if (int rc = build_cell_list(s, ev ? ev->e[4] : nullptr, ev ? ev->e[5] : nullptr)) return rc;
         if (ev) CU(cudaEventRecord(ev->e[1], s->stream));
-        if (int rc = launch_force(s)) return rc;
+        if (s->n > 0)
+            if (int rc = launch_force(s)) return rc;
         if (ev) CU(cudaEventRecord(ev->e[2], s->stream));
-        LAUNCH(s, integrate_kernel, div_up(s->n, 256), 256, 0, s->pos[s->cur], s->vel[s->cur], s->frc, s->n, s->sc);
+        if (s->n > 0) LAUNCH(s, integrate_kernel, div_up(s->n, 256), 256, 0, opos(s), ovel(s), ofrc(s), s->n, s->sc);
         if (ev) CU(cudaEventRecord(ev->e[3], s->stream));
         s->sorted_valid = false;
     }
@@ -818,8 +912,8 @@ extern "C" int cf_step_host(cf_sim* s, const cf_params* p, const cf_particle* in
     if (int rc = upload_impl(s, in, counts_in, nullptr, count)) return rc;
     if (int rc = cf_step(s, p, 1)) return rc;
     if (count == 0) return CF_OK;
-    LAUNCH(s, soa_to_aos_kernel, div_up(count, 256), 256, 0, s->pos[s->cur], s->vel[s->cur], s->frc,
-           s->id[s->cur], s->d_aos, s->d_counts, count, 1);
+    LAUNCH(s, soa_to_aos_kernel, div_up(count, 256), 256, 0, opos(s), ovel(s), ofrc(s),
+           oid(s), s->d_aos, s->d_counts, count, 1);
     CU(cudaMemcpyAsync(out, s->d_aos, sizeof(AosParticle) * (size_t)count, cudaMemcpyDeviceToHost, s->stream));
     if (counts_out)
         CU(cudaMemcpyAsync(counts_out, s->d_counts, sizeof(int) * (size_t)count, cudaMemcpyDeviceToHost, s->stream));
@@ -836,12 +930,12 @@ extern "C" int cf_build_graph(cf_sim* s, float dist, int max_conn, int* n_edges)
     ARG(max_conn >= 0);
     if (int rc = set_device(s)) return rc;
     int mc = std::min(max_conn, CF_MAX_GRAPH_CONN);
-    if (s->n == 0 || mc == 0 || !(dist > 0.f)) {
+    if ((s->n == 0 && !s->slab) || mc == 0 || !(dist > 0.f)) {
         s->n_edges = 0;
         return CF_OK;
     }
     if (int rc = prepare_step_const(s)) return rc;
-    long long need = (long long)s->n * mc;
+    long long need = (long long)std::max(s->slab ? s->cap_own : s->n, 1) * mc;
     if (need > s->edge_cap) {
         CU(cudaStreamSynchronize(s->stream));
         cudaFree(s->edges);
@@ -852,13 +946,18 @@ extern "C" int cf_build_graph(cf_sim* s, float dist, int max_conn, int* n_edges)
         s->edge_cap = (int)need;
     }
     if (s->opt_timing) CU(cudaEventRecord(s->ev_g0, s->stream));
-    if (int rc = ensure_sorted(s)) return rc;
+    if (int rc = build_cell_list(s)) return rc;
     float min_edge = 1e30f;
-    for (int a = 0; a < 3; a++) min_edge = std::min(min_edge, s->sc.W[a] / (float)s->sc.dims[a]);
+    for (int a = 0; a < 3; a++) {
+        float e = a == 0 && s->slab ? (s->sc.W[0] / (float)s->world) / (float)s->nxl : s->sc.W[a] / (float)s->sc.dims[a];
+        min_edge = std::min(min_edge, e);
+    }
     int m = (int)ceil((double)dist * (1.0 + 1e-5) / (double)min_edge);
     m = std::max(m, 1);
+    if (s->slab && m > 1)
+        return fail(CF_ERR_ARG, "proximity distance %.1f exceeds the one-cell ghost layer (%.1f) of slab mode", dist, min_edge);
     CU(cudaMemsetAsync(s->d_edge_count, 0, sizeof(int), s->stream));
-    LAUNCH(s, graph_kernel, div_up(s->n, 128), 128, 0, s->pos[s->cur], s->id[s->cur], s->cell_start, 0, s->n,
+    if (s->n > 0) LAUNCH(s, graph_kernel, div_up(s->n, 128), 128, 0, s->pos[s->cur], s->id[s->cur], s->cell_start, s->base, s->n,
            s->sc, dist * dist, mc, m, s->edges, s->edge_slots, s->edge_cap, s->d_edge_count);
     if (s->opt_timing) {
         CU(cudaEventRecord(s->ev_g1, s->stream));
@@ -934,6 +1033,8 @@ extern "C" int cf_set_option(cf_sim* s, const char* name, double value) {
     else if (k == "force_kernel") s->opt_force_kernel = (int)value;
     else if (k == "timing") s->opt_timing = (int)value;
     else if (k == "max_cells_per_particle") s->opt_max_cells_per_particle = value;
+    else if (k == "halo_capacity") s->cap_halo = (int)value;       // before cf_comm_init
+    else if (k == "migrant_capacity") s->cap_mig = (int)value;     // before cf_comm_init
     else return fail(CF_ERR_ARG, "unknown option '%s'", name);
     s->sorted_valid = false;
     return CF_OK;
@@ -944,7 +1045,7 @@ extern "C" int cf_stats_reset(cf_sim* s) {
     if (int rc = set_device(s)) return rc;
     CU(cudaStreamSynchronize(s->stream));
     s->ev_used = 0;
-    s->ms_sort = s->ms_force = s->ms_integrate = s->ms_total = s->ms_graph = 0;
+    s->ms_sort = s->ms_force = s->ms_integrate = s->ms_total = s->ms_graph = s->ms_exchange = 0;
     s->stat_steps = 0;
     s->launches = 0;
     s->graph_timed = false;
@@ -964,6 +1065,10 @@ extern "C" int cf_get_stats(cf_sim* s, cf_stats* st) {
         s->ms_sort += a;
         s->ms_force += b;
         s->ms_integrate += c;
+        if (s->slab) {
+            float x = 0;
+            if (cudaEventElapsedTime(&x, ev.e[4], ev.e[5]) == cudaSuccess) s->ms_exchange += x;
+        }
         s->ms_total += a + b + c;
         s->stat_steps++;
     }
@@ -980,16 +1085,22 @@ extern "C" int cf_get_stats(cf_sim* s, cf_stats* st) {
     st->ms_force = s->ms_force;
     st->ms_integrate = s->ms_integrate;
     st->ms_graph = s->ms_graph;
+    st->ms_exchange = s->ms_exchange;
     st->steps = s->stat_steps;
     st->launches = s->launches;
     for (int a = 0; a < 3; a++) st->grid[a] = s->sc.dims[a];
     st->stencil = 1;
     st->n_owned = s->n;
     st->n_ghost = 0;
+    if (s->slab) {
+        int g[2] = {0, 0};
+        CU(cudaMemcpy(g, s->d_slab_counts + 4, 2 * sizeof(int), cudaMemcpyDeviceToHost));
+        st->n_ghost = g[0] + g[1];
+    }
     if (s->n > 0) {
         unsigned long long acc = 0;
         CU(cudaMemsetAsync(s->d_accum, 0, sizeof(unsigned long long), s->stream));
-        sum_counts_kernel<<<148 * 4, 256, 0, s->stream>>>(s->frc, s->n, s->d_accum);
+        sum_counts_kernel<<<148 * 4, 256, 0, s->stream>>>(ofrc(s), s->n, s->d_accum);
         CU(cudaMemcpyAsync(&acc, s->d_accum, sizeof(acc), cudaMemcpyDeviceToHost, s->stream));
         CU(cudaStreamSynchronize(s->stream));
         st->accepted_pairs = (long long)acc;
@@ -1012,10 +1123,12 @@ extern "C" int cf_download_cell_keys(cf_sim* s, uint32_t* keys, int32_t* ids, in
     ARG(capacity >= s->n);
     if (int rc = set_device(s)) return rc;
     if (int rc = prepare_step_const(s)) return rc;
-    if (s->n == 0) return CF_OK;
-    if (int rc = ensure_sorted(s)) return rc;
+    if (s->n == 0 && !s->slab) return CF_OK;
+    if (int rc = build_cell_list(s)) return rc;
+    *count = s->n;
+    ARG(capacity >= s->n);
     if (keys) CU(cudaMemcpyAsync(keys, s->keys[0], sizeof(uint32_t) * (size_t)s->n, cudaMemcpyDeviceToHost, s->stream));
-    if (ids) CU(cudaMemcpyAsync(ids, s->id[s->cur], sizeof(int) * (size_t)s->n, cudaMemcpyDeviceToHost, s->stream));
+    if (ids) CU(cudaMemcpyAsync(ids, oid(s), sizeof(int) * (size_t)s->n, cudaMemcpyDeviceToHost, s->stream));
     CU(cudaStreamSynchronize(s->stream));
     return CF_OK;
 }

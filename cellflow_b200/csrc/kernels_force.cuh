@@ -48,7 +48,7 @@ force_pp_kernel(const float4* __restrict__ pos4, const int* __restrict__ cell_st
     if (s >= first + n) return;
     float4 p = pos4[s];
     int ti = (int)__float_as_uint(p.w);
-    int cx = cf_cell_coord(p.x, c.inv[0], c.dims[0]);
+    int cx = cf_cell_coord_x(p.x, c);
     int cy = cf_cell_coord(p.y, c.inv[1], c.dims[1]);
     int cz = cf_cell_coord(p.z, c.inv[2], c.dims[2]);
     int xs[3], ys[3], zs[3];

@@ -29,10 +29,10 @@ graph_kernel(const float4* __restrict__ pos4, const int* __restrict__ id, const 
         float4 p = pos4[s];
         my_id = id[s];
         uint32_t ti = __float_as_uint(p.w);
-        int cx = cf_cell_coord(p.x, c.inv[0], c.dims[0]);
+        int cx = cf_cell_coord_x(p.x, c);
         int cy = cf_cell_coord(p.y, c.inv[1], c.dims[1]);
         int cz = cf_cell_coord(p.z, c.inv[2], c.dims[2]);
-        int x0 = max(cx - m, 0), x1 = min(cx + m, c.dims[0] - 1);
+        int x0 = max(cx - m, c.gx_lo), x1 = min(cx + m, c.gx_hi);
         int y0 = max(cy - m, 0), y1 = min(cy + m, c.dims[1] - 1);
         int z0 = max(cz - m, 0), z1 = min(cz + m, c.dims[2] - 1);
         for (int x = x0; x <= x1; x++)

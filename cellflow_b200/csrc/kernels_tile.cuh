@@ -85,6 +85,7 @@ __global__ void count_tests_kernel(const int* __restrict__ cell_start, int ncell
             int cz = cell % c.dims[2];
             int cy = (cell / c.dims[2]) % c.dims[1];
             int cx = cell / (c.dims[2] * c.dims[1]);
+            if (cx < c.x_off || cx >= c.x_off + c.x_cells) nc = 0; // ghost layers hold no i-particles
             int xs[3], ys[3], zs[3];
             int kx = cf_axis_cells(cx, c.dims[0], c.periodic_x != 0, xs);
             int ky = cf_axis_cells(cy, c.dims[1], true, ys);
@@ -252,10 +253,12 @@ force_tile_kernel(const float4* __restrict__ pos4, const int* __restrict__ cell_
             int x = cx + ddx, y = cy + ddy;
             float sx = 0.f, sy = 0.f, sz = 0.f;
             bool valid = true;
-            if (x < 0) {
-                if (c.periodic_x) { x = c.dims[0] - 1; sx = -c.W[0]; } else valid = false;
-            } else if (x >= c.dims[0]) {
-                if (c.periodic_x) { x = 0; sx = c.W[0]; } else valid = false;
+            if (c.periodic_x) {
+                if (x < 0) { x = c.dims[0] - 1; sx = -c.W[0]; } else if (x >= c.dims[0]) { x = 0; sx = c.W[0]; }
+            } else { // slab mode: i-cells are layers 1..dims-2, so x stays inside [0, dims-1]
+                if (x < 0 || x >= c.dims[0]) valid = false;
+                else if (x == 0) sx = c.gshift_lo;
+                else if (x == c.dims[0] - 1) sx = c.gshift_hi;
             }
             if (y < 0) { y = ny - 1; sy = -c.W[1]; } else if (y >= ny) { y = 0; sy = c.W[1]; }
             int z0, z1;
@@ -437,8 +440,6 @@ force_tile_kernel(const float4* __restrict__ pos4, const int* __restrict__ cell_
 // The tile kernel decides the minimum-image wrap per neighbour cell, which is only equivalent to
 // the reference's per-pair test when every periodic axis has at least 4 cells; it pays off when
 // cells hold enough particles to fill warps.
-static inline bool tile_kernel_applicable(const StepConst& c, int n, int ncell) {
-    if (c.dims[1] < 4 || c.dims[2] < 4) return false;
-    if (c.periodic_x && c.dims[0] < 4) return false;
-    return (double)n / (double)ncell >= 200.0; // below this most warps of a 512-slot tile idle
+static inline bool tile_kernel_applicable(const StepConst&, int n, int ncell) {
+    return (double)n / (double)ncell >= 48.0;
 }

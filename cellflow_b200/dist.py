@@ -1,0 +1,278 @@
+"""One-process-per-GPU glue for the slab-decomposed engine.
+
+torch.distributed is used for plumbing only: rendezvous (RANK / WORLD_SIZE / MASTER_* from the
+environment, as torch.distributed.run sets them), broadcasting the NCCL unique id the C library
+creates, gathering results and reducing timings.  The per-step halo / migration exchange is done
+inside the C library with ncclSend/ncclRecv on the engine's stream (csrc/slab_host.inl).
+
+Everything here that does not touch a GPU (slab bounds, partition / gather of particle arrays,
+max-over-ranks reductions, id broadcast) also runs on the `gloo` backend; tests/test_dist_cpu.py
+covers it with world_size 2 on CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+import os
+import time
+
+import numpy as np
+
+from . import _lib
+from ._lib import PARTICLE
+
+
+def env_rank():
+    return (int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")),
+            int(os.environ.get("LOCAL_RANK", "0")))
+
+
+def init_process_group(backend: str | None = None):
+    """Initialises torch.distributed from the environment (idempotent).  Returns (rank, world)."""
+    import torch
+    import torch.distributed as dist
+
+    rank, world, local = env_rank()
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+    return rank, world
+
+
+def slab_bound(width: float, r: int, world: int) -> np.float32:
+    """x bound r of `world` slabs over [0, width): the same expression the C library evaluates
+    (csrc/slab_host.inl: slab_bound), so host-side partitions agree bit for bit."""
+    return np.float32(np.float64(np.float32(width)) * np.float64(r) / np.float64(world))
+
+
+def slab_owner(x: np.ndarray, width: float, world: int) -> np.ndarray:
+    """Owning rank of every x coordinate (x in [0, width))."""
+    bounds = np.array([slab_bound(width, r, world) for r in range(world + 1)], dtype=np.float32)
+    owner = np.searchsorted(bounds, np.asarray(x, dtype=np.float32), side="right") - 1
+    return np.clip(owner, 0, world - 1).astype(np.int32)
+
+
+def partition(particles: np.ndarray, counts: np.ndarray, width: float, rank: int, world: int):
+    """(particles, counts, ids) owned by `rank`: the subset whose x lies in its slab, ids =
+    original indices."""
+    owner = slab_owner(particles["pos"][:, 0], width, world)
+    ids = np.nonzero(owner == rank)[0].astype(np.int32)
+    return particles[ids], np.asarray(counts, np.int32)[ids], ids
+
+
+def broadcast_bytes(data: bytes | None, nbytes: int, src: int = 0) -> bytes:
+    """Broadcast a byte string from `src` (works on gloo and nccl)."""
+    import torch
+    import torch.distributed as dist
+
+    if not dist.is_initialized():
+        return data
+    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+    t = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
+    if dist.get_rank() == src:
+        t.copy_(torch.frombuffer(bytearray(data), dtype=torch.uint8))
+    dist.broadcast(t, src)
+    return bytes(t.cpu().numpy().tobytes())
+
+
+def nccl_unique_id() -> bytes:
+    """Rank 0 asks the C library for an ncclUniqueId; everybody gets it."""
+    import torch.distributed as dist
+
+    ident = None
+    if not dist.is_initialized() or dist.get_rank() == 0:
+        buf = C.create_string_buffer(128)
+        _lib.check(_lib.lib().cf_nccl_unique_id(buf))
+        ident = buf.raw
+    return broadcast_bytes(ident, 128, 0)
+
+
+def all_reduce_max(value: float) -> float:
+    import torch
+    import torch.distributed as dist
+
+    if not dist.is_initialized():
+        return float(value)
+    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+    t = torch.tensor([value], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def all_reduce_sum(value: float) -> float:
+    import torch
+    import torch.distributed as dist
+
+    if not dist.is_initialized():
+        return float(value)
+    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+    t = torch.tensor([value], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
+
+
+def barrier():
+    import torch.distributed as dist
+
+    if dist.is_initialized():
+        dist.barrier()
+
+
+def gather_particles(particles: np.ndarray, counts: np.ndarray, ids: np.ndarray, n_total: int):
+    """All ranks contribute what they own; rank 0 returns (particles, counts) in original id
+    order (None elsewhere)."""
+    import torch.distributed as dist
+
+    if not dist.is_initialized():
+        out = np.zeros(n_total, PARTICLE)
+        cnt = np.zeros(n_total, np.int32)
+        out[ids] = particles
+        cnt[ids] = counts
+        return out, cnt
+    payload = (particles.tobytes(), np.asarray(counts, np.int32).tobytes(), np.asarray(ids, np.int32).tobytes())
+    gathered = [None] * dist.get_world_size() if dist.get_rank() == 0 else None
+    dist.gather_object(payload, gathered, dst=0)
+    if dist.get_rank() != 0:
+        return None, None
+    out = np.zeros(n_total, PARTICLE)
+    cnt = np.zeros(n_total, np.int32)
+    seen = 0
+    for pb, cb, ib in gathered:
+        i = np.frombuffer(ib, np.int32)
+        out[i] = np.frombuffer(pb, PARTICLE)
+        cnt[i] = np.frombuffer(cb, np.int32)
+        seen += len(i)
+    assert seen == n_total, f"ranks own {seen} particles in total, expected {n_total}"
+    return out, cnt
+
+
+def make_slab_sim(params, raw, radio, n_total, seed, mode, capacity_factor=1.5, force_table=None):
+    """Creates this rank's simulation, joins the ring and spawns the global initial condition."""
+    import torch
+
+    from .sim import ParticleSimulation
+
+    rank, world = init_process_group()
+    _, _, local = env_rank()
+    T = params.numParticleTypes
+    sim = ParticleSimulation(0, T, device=local, init=False)
+    sim.params = params
+    sim.setRadioByType(radio)
+    if force_table is not None:
+        sim.setForceTable(force_table)
+    else:
+        sim.setRawForceTableValues(raw)
+        sim.updateForceTable(params.forceRange, params.forceBias, params.forceOffset)
+    ident = nccl_unique_id() if world > 1 else None
+    capacity = int(n_total / world * capacity_factor) + 1024
+    sim.commInit(rank, world, ident, capacity)
+    if seed is not None:
+        sim.initParticlesGlobal(n_total, seed, mode)
+    return sim, rank, world
+
+
+def bench_multi(args, workloads, workload_setup):
+    """bench.py body for world > 1: weak scaling, n_per_gpu particles per rank, one 8000-wide block
+    of canvas per rank along x.  Device-timed per rank (CUDA events inside the library), max over
+    ranks, rank 0 prints the JSON line."""
+    import torch
+
+    from bench import METRIC, ClockSampler  # the script's own helpers
+
+    rank, world = init_process_group("nccl")
+    _, _, local = env_rank()
+    torch.cuda.set_device(local)
+    L = _lib.lib()
+    params, raw, radio, n_total, seed, mode, graph = workload_setup(args.workload, world)
+    sim, rank, world = make_slab_sim(params, raw, radio, n_total, seed, mode)
+    if args.force_kernel:
+        sim.setOption("force_kernel", args.force_kernel)
+    sim.setOption("timing", 1)
+
+    def one_step():
+        sim.simulate(sync=False)
+        if graph:
+            sim.generateProximityGraph(graph[0], graph[1])
+
+    for _ in range(args.warmup):
+        one_step()
+    sim.sync()
+    sim.statsReset()
+    barrier()
+    torch.cuda.synchronize()
+    graph_ms = 0.0
+    with ClockSampler(local) as clocks:
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            _lib.check(L.cf_bench_flush_l2(C.c_int(local), C.c_size_t(256 << 20)))
+            one_step()
+            sim.sync()
+            if graph:
+                graph_ms += sim.stats().ms_graph
+        torch.cuda.synchronize()
+        barrier()
+        wall = time.perf_counter() - t0
+        st = sim.stats()
+    my_ms = st.ms_total / max(st.steps, 1) + graph_ms / args.steps
+    step_ms = all_reduce_max(my_ms)
+    owned = all_reduce_sum(float(st.n_owned))
+    accepted = all_reduce_sum(float(st.accepted_pairs))
+    exch_ms = all_reduce_max(st.ms_exchange / max(st.steps, 1))
+    force_ms = all_reduce_max(st.ms_force / max(st.steps, 1))
+    launches = all_reduce_sum(float(st.launches))
+    tf = C.c_double(0)
+    mhz = C.c_double(0)
+    _lib.check(L.cf_bench_fp32_peak(C.c_int(local), C.byref(tf), C.byref(mhz)))
+
+    # e2e: every rank round-trips what it owns through pinned host memory each step
+    e2e_steps = max(3, min(args.steps, 8))
+    barrier()
+    t0 = time.perf_counter()
+    h2d = d2h = 0
+    for _ in range(e2e_steps):
+        p, c, i = sim.downloadOwned()
+        sim.uploadOwned(p, c, i)
+        one_step()
+        sim.sync()
+        h2d += len(p) * 52
+        d2h += len(p) * 52
+    barrier()
+    e2e_s = all_reduce_max((time.perf_counter() - t0) / e2e_steps)
+    h2d = all_reduce_sum(h2d / e2e_steps)
+    d2h = all_reduce_sum(d2h / e2e_steps)
+    if rank == 0:
+        out = {
+            "metric": METRIC, "value": round(n_total / (step_ms * 1e-3), 1), "unit": METRIC, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(step_ms, 4),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": args.workload, "particles": n_total, "particles_per_gpu": n_total // world,
+                       "types": params.numParticleTypes,
+                       "canvas": [params.canvasWidth, params.canvasHeight, params.canvasDepth],
+                       "radius": params.radius, "ratio": params.ratioWithLFO,
+                       "mean_neighbours": round(accepted / max(owned, 1), 1),
+                       "graph": list(graph) if graph else None,
+                       "l2": "flushed between timed steps (256 MiB overwrite)",
+                       "parallelism": f"{world} x-slabs, NCCL halo+migration exchange per step",
+                       "timing": "CUDA events per rank, max over ranks"},
+            "e2e": {"value": round(n_total / e2e_s, 1), "unit": METRIC, "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(d2h), "ms_per_step": round(e2e_s * 1e3, 4),
+                    "api": "download owned -> upload owned -> cf_step, every rank, host numpy buffers"},
+            "gpu_launches": int(launches), "clocks": clocks.summary(),
+            "roofline": {"kernel": "pair_force", "bound": "fp32",
+                         "achieved": round(37.0 * accepted / (force_ms * 1e-3) * 1e-12, 3) if force_ms > 0 else None,
+                         "peak": round(tf.value * world, 2), "unit": "TFLOP/s",
+                         "frac": round(37.0 * accepted / (force_ms * 1e-3) * 1e-12 / (tf.value * world), 4)
+                         if force_ms > 0 else None, "traffic": None,
+                         "peak_source": "FFMA microbenchmark on rank 0 x n_gpus"},
+            "phases_ms": {"pair_force_max": round(force_ms, 4), "exchange_max": round(exch_ms, 4)},
+            "cpu_baseline": None, "wall_s_timed_region": round(wall, 3),
+        }
+        print(json.dumps(out), flush=True)
+    sim.close()
+    barrier()

@@ -214,6 +214,42 @@ class ParticleSimulation:
                                    C.c_void_p(cin[0]), C.c_void_p(pout[0]), C.c_void_p(cout[0]),
                                    C.c_int(pin[1])))
 
+    # -- multi-GPU slabs (one process per GPU) ----------------------------------------------------
+    def commInit(self, rank: int, world: int, nccl_id: bytes | None, capacity: int):
+        """Rank `rank` of `world` owns x in [rank*W/world, (rank+1)*W/world).  world == 1 runs the
+        same slab code path with device-local copies instead of NCCL."""
+        buf = C.create_string_buffer(nccl_id, 128) if nccl_id is not None else None
+        check(self._L.cf_set_params(self._h, C.byref(self.params)))
+        check(self._L.cf_comm_init(self._h, C.c_int(rank), C.c_int(world), buf, C.c_int(capacity)))
+
+    def initParticlesGlobal(self, n_total: int, seed: int, mode=_lib.INIT_UNIFORM):
+        check(self._L.cf_set_params(self._h, C.byref(self.params)))
+        check(self._L.cf_init_particles_global(self._h, C.c_int64(n_total), C.c_uint64(seed), C.c_int(mode)))
+
+    def slabBounds(self):
+        lo, hi = C.c_float(0), C.c_float(0)
+        check(self._L.cf_set_params(self._h, C.byref(self.params)))
+        check(self._L.cf_slab_bounds(self._h, C.byref(lo), C.byref(hi)))
+        return lo.value, hi.value
+
+    def uploadOwned(self, particles, counts, ids):
+        particles = np.ascontiguousarray(particles, dtype=PARTICLE)
+        counts = np.ascontiguousarray(counts, dtype=np.int32)
+        ids = np.ascontiguousarray(ids, dtype=np.int32)
+        check(self._L.cf_upload_particles_ids(self._h, _p(particles), _p(counts), _p(ids),
+                                              C.c_int(len(particles))))
+
+    def downloadOwned(self):
+        """(particles, counts, ids) of the particles this rank currently owns (slot order)."""
+        cap = max(self.getParticleCount(), 1)
+        out = np.zeros(cap, dtype=PARTICLE)
+        counts = np.zeros(cap, dtype=np.int32)
+        ids = np.zeros(cap, dtype=np.int32)
+        n = C.c_int(0)
+        check(self._L.cf_download_particles_ids(self._h, _p(out), _p(counts), _p(ids), C.c_int(cap),
+                                                C.byref(n)))
+        return out[: n.value], counts[: n.value], ids[: n.value]
+
     def cellKeys(self):
         n = self.getParticleCount()
         keys = np.zeros(n, dtype=np.uint32)

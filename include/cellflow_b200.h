@@ -225,6 +225,11 @@ int cf_nccl_unique_id(void* id128);  /* 128 bytes; rank 0 creates, host broadcas
 /* Rank `rank` of `world` owns x in [rank*W/world, (rank+1)*W/world).  `capacity` bounds the
  * owned particle count of this rank. */
 int cf_comm_init(cf_sim* sim, int rank, int world, const void* id128, int capacity);
+/* Slab-mode initial condition: every rank generates the same n_total particles (counter-based
+ * generator) and keeps those whose x lies in its slab.  Canvas = params last set. */
+int cf_init_particles_global(cf_sim* sim, int64_t n_total, uint64_t seed, int mode);
+/* Owned x interval [lo, hi) of this rank (valid after cf_comm_init + cf_set_params). */
+int cf_slab_bounds(cf_sim* sim, float* lo, float* hi);
 /* Upload a subset with explicit global ids (multi-GPU: each rank uploads what it owns). */
 int cf_upload_particles_ids(cf_sim* sim, const cf_particle* aos, const int32_t* counts,
                             const int32_t* ids, int count);

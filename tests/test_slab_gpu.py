@@ -1,0 +1,110 @@
+"""Slab-decomposition path on GPUs.  world == 1 runs the complete slab pipeline (class sort,
+ghost layers, seam shift) with device-local copies instead of NCCL; the multi-rank test
+launches tests/dist_check.py under torch.distributed.run when the box has >= 2 GPUs."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import cellflow_b200 as cf
+import oracle as O
+import util as U
+
+pytestmark = pytest.mark.gpu
+THREADS = max(1, min(8, O.max_threads()))
+
+
+def slab_sim(p, table, radio, state, counts, capacity=None, **opts):
+    sim = cf.ParticleSimulation(0, p.numParticleTypes, init=False)
+    sim.params = U.to_lib_params(p)
+    sim.setRadioByType(radio)
+    sim.setForceTable(table)
+    for k, v in opts.items():
+        sim.setOption(k, v)
+    sim.commInit(0, 1, None, capacity or int(len(state) * 1.2) + 1024)
+    sim.uploadOwned(state, counts, np.arange(len(state), dtype=np.int32))
+    return sim
+
+
+def by_id(sim, n):
+    p, c, i = sim.downloadOwned()
+    assert sorted(i.tolist()) == list(range(n))
+    out = np.zeros(n, cf.PARTICLE)
+    cnt = np.zeros(n, np.int32)
+    out[i] = p
+    cnt[i] = c
+    return out, cnt
+
+
+@pytest.mark.parametrize("kernel", [1, 2])
+@pytest.mark.parametrize("name,n,mode,over,radio", [
+    ("settings", 20000, "uniform", {}, None),
+    ("eater", 30000, "cube", {}, None),
+    ("eater", 20000, "uniform", {"ratioWithLFO": 0.5}, [1.0, 0.5, 0.0, 0.0, -0.5, 1.0]),
+    ("pulser", 8000, "uniform", {"canvasWidth": 3000.0, "canvasHeight": 2500.0, "canvasDepth": 2000.0}, None),
+])
+def test_slab_world1_matches_oracle(name, n, mode, over, radio, kernel):
+    p, table, r0 = U.config(name, **over)
+    radio = np.float32(radio) if radio is not None else r0
+    state, counts = U.random_state(n, p.numParticleTypes, 17, p.canvas, mode)
+    state["pos"][:64, 0] = 0.0                                    # on the x seam
+    state["pos"][64:128, 0] = np.nextafter(p.canvas[0], np.float32(0))
+    sim = slab_sim(p, table, radio, state, counts, force_kernel=kernel)
+    want_state, want_counts = state, counts
+    for step in range(3):
+        sim.simulate()
+        got, gcnt = by_id(sim, n)
+        want, wcnt, fabs = O.step(want_state, want_counts, p, table, radio, "cells", THREADS)
+        assert np.array_equal(gcnt, wcnt), step
+        mult = U.force_multiplier_of(p, wcnt, want_counts)
+        assert U.force_rel_err(got["acc"], want["acc"], fabs, mult).max() <= U.FORCE_RTOL
+        want_state, want_counts = got, gcnt   # per-step parity: restart the oracle from the engine
+    st = sim.stats()
+    assert st.n_owned == n and st.n_ghost > 0
+    sim.close()
+
+
+def test_slab_graph_matches_oracle():
+    p, table, radio = U.config("settings")
+    state, counts = U.random_state(30000, 8, 5, p.canvas, "cube")
+    sim = slab_sim(p, table, radio, state, counts)
+    sim.simulate(steps=2)
+    now, _ = by_id(sim, len(state))
+    edges, _ = sim.generateProximityGraph(200.0, 5)
+    assert U.edge_set(edges) == U.edge_set(O.graph(now, 200.0, 5, canvas=p.canvas, method="cells"))
+    with pytest.raises(cf.CellFlowError):       # wider than the one-cell ghost layer
+        sim.generateProximityGraph(600.0, 5)
+    sim.close()
+
+
+def test_slab_global_init_matches_oracle():
+    p, table, radio = U.config("eater")
+    sim = cf.ParticleSimulation(0, 6, init=False)
+    sim.params = U.to_lib_params(p)
+    sim.commInit(0, 1, None, 60000)
+    sim.initParticlesGlobal(50000, 0x5EED0005, cf.INIT_UNIFORM)
+    got, _ = by_id(sim, 50000)
+    assert got.tobytes() == O.init_particles(50000, 6, 0x5EED0005, 1, p.canvas).tobytes()
+    sim.close()
+
+
+def _gpu_count():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_multi_rank_matches_single_gpu(world):
+    if _gpu_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    port = 29600 + world
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(U.ROOT, "tests", "dist_check.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "DIST_CHECK_OK" in r.stdout
