@@ -27,12 +27,10 @@ def main():
     mine, mcounts, ids = cfd.partition(state, counts, p.canvasWidth, rank, world)
     sim.uploadOwned(mine, mcounts, ids)
     want_state, want_counts = state, counts
-    migrated = 0
+    first_ids = set(ids.tolist())
     for step in range(4):
-        before_ids = set(sim.downloadOwned()[2].tolist())
         sim.simulate()
         pp, cc, ii = sim.downloadOwned()
-        migrated += len(set(ii.tolist()) - before_ids)
         got, gcnt = cfd.gather_particles(pp, cc, ii, n)
         edges, _ = sim.generateProximityGraph(200.0, 5)
         import torch.distributed as dist
@@ -51,10 +49,11 @@ def main():
             assert es == U.edge_set(O.graph(got, 200.0, 5, canvas=p.canvas, method="cells")), f"step {step}: edges"
             want_state, want_counts = got, gcnt
         # every rank continues from its own device state (no re-upload): real migration
-    total_migrated = cfd.all_reduce_sum(float(migrated))
-    owner_ok = 1.0
+    # migration is applied by the cell-list build that follows a step (the graph build above)
+    pp, _, ii = sim.downloadOwned()
+    total_migrated = cfd.all_reduce_sum(float(len(set(ii.tolist()) - first_ids)))
     lo, hi = sim.slabBounds()
-    pp, _, _ = sim.downloadOwned()
+    assert np.all((pp["pos"][:, 0] >= lo) & (pp["pos"][:, 0] < hi)), "a rank holds a particle outside its slab"
     st = sim.stats()
     if rank == 0:
         assert total_migrated > 0, "test did not exercise migration"
