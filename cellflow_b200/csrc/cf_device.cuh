@@ -66,6 +66,31 @@ __device__ __forceinline__ uint32_t cf_cell_key(float4 p, const StepConst& c) {
     return (uint32_t)((cx * c.dims[1] + cy) * c.dims[2] + cz);
 }
 
+// Sort key = cell * 64 + Morton code of the particle's 4x4x4 sub-cell.  Inside a cell, particles
+// that are adjacent in memory are adjacent in space, so the 32 i-particles of a warp and every
+// 32-particle word of the j stream are compact blobs: whole (warp, word) pairs are in range or
+// out of range together and the lanes of a warp accept similar numbers of neighbours.
+// The cell part is exactly cf_cell_key (4*y truncates to 4*trunc(y) + sub for y >= 0).
+#define CF_KEY_SUB 64u
+__device__ __forceinline__ int cf_sub_coord(float y, int cell, int n) {
+    int f = (int)__fmul_rn(y, 4.0f);
+    f = f > 4 * n - 1 ? 4 * n - 1 : f;
+    int sub = f - 4 * cell;
+    return sub < 0 ? 0 : (sub > 3 ? 3 : sub);
+}
+__device__ __forceinline__ uint32_t cf_spread2(uint32_t v) { return (v & 1u) | ((v & 2u) << 2); }
+__device__ __forceinline__ uint32_t cf_sort_key(float4 p, const StepConst& c) {
+    float yx = __fmul_rn(__fsub_rn(p.x, c.x_org), c.inv[0]);
+    float yy = __fmul_rn(p.y, c.inv[1]), yz = __fmul_rn(p.z, c.inv[2]);
+    int cx = cf_cell_coord_x(p.x, c), cy = cf_cell_coord(p.y, c.inv[1], c.dims[1]),
+        cz = cf_cell_coord(p.z, c.inv[2], c.dims[2]);
+    uint32_t sx = (uint32_t)cf_sub_coord(yx, cx - c.x_off, c.x_cells);
+    uint32_t sy = (uint32_t)cf_sub_coord(yy, cy, c.dims[1]);
+    uint32_t sz = (uint32_t)cf_sub_coord(yz, cz, c.dims[2]);
+    uint32_t cell = (uint32_t)((cx * c.dims[1] + cy) * c.dims[2] + cz);
+    return cell * CF_KEY_SUB + (cf_spread2(sz) | (cf_spread2(sy) << 1) | (cf_spread2(sx) << 2));
+}
+
 // Minimum-image wrap exactly as the reference: two dependent tests (.cu:97-98).  Both
 // additions are exact in fp32 (Sterbenz), so any formulation of the same decision is bit-equal.
 __device__ __forceinline__ float cf_wrap(float d, float W, float half, float nhalf) {

@@ -353,7 +353,7 @@ static int prepare_step_const(cf_sim* s) {
     // the grid has at most opt_max_cells_per_particle * n cells
     double vol = (double)W[0] * W[1] * W[2] / (s->slab ? s->world : 1);
     double max_cells = std::max(64.0, s->opt_max_cells_per_particle * (double)std::max(s->n, 1));
-    max_cells = std::min(max_cells, 16777216.0); // cell * T + type must fit the 32-bit sort key
+    max_cells = std::min(max_cells, 16777216.0); // class * ncell * 64 must fit the 32-bit sort key
     double edge = std::max((double)rmax * (1.0 + 1e-5), cbrt(vol / max_cells));
     if (!(edge > 0.0)) edge = cbrt(vol / max_cells);
     long long ncell = 1;
@@ -438,7 +438,7 @@ static int ensure_sorted(cf_sim* s) {
     int blocks = div_up(n, 256);
     LAUNCH(s, cell_key_kernel, blocks, 256, 0, s->pos[cur], s->keys[0], s->vals[0], n, s->sc);
     int bits = 1;
-    while ((1ll << bits) < (long long)s->ncell * s->T) bits++;
+    while ((1ll << bits) < (long long)s->ncell * CF_KEY_SUB) bits++;
     int passes = div_up(bits, 8);
     int bits_per_pass = div_up(bits, passes);
     int items = 4096;
@@ -464,7 +464,7 @@ static int ensure_sorted(cf_sim* s) {
     LAUNCH(s, reorder_kernel, blocks, 256, 0, s->vals[src], s->pos[cur], s->vel[cur], s->id[cur],
            s->pos[nxt], s->vel[nxt], s->id[nxt], n);
     LAUNCH(s, cell_bounds_kernel, div_up(s->ncell + 1, 256), 256, 0, s->keys[src], n, s->cell_start,
-           s->ncell, 0, s->T);
+           s->ncell, 0);
     if (src != 0) std::swap(s->keys[0], s->keys[1]), std::swap(s->vals[0], s->vals[1]);
     // keys[0] now holds the sorted keys of the current order
     s->cur = nxt;

@@ -22,7 +22,7 @@ struct SlabGeom {
     float x_lo, x_hi;   // owned interval (global coordinates), x_hi == neighbour's x_lo bit for bit
     float slab_w;       // x_hi - x_lo in real terms (W / G)
     float W;            // global width
-    uint32_t class_stride; // keys per class = ncell * T
+    uint32_t class_stride; // keys per class = ncell * 64
 };
 
 // Fixed-capacity messages with the element count in-band (no size exchange, no host sync):
@@ -48,7 +48,7 @@ __device__ __forceinline__ uint32_t slab_class(float x, const SlabGeom& g, int* 
     return SLAB_STAY;
 }
 
-// key = class * (ncell*T) + cell*T + type for owned particle i (slots base+i), val = i.
+// key = class * (ncell*64) + cf_sort_key for owned particle i (slots base+i), val = i.
 __global__ void slab_key_kernel(const float4* __restrict__ pos4, uint32_t* __restrict__ keys,
                                 uint32_t* __restrict__ vals, int n, StepConst c, SlabGeom g,
                                 int* __restrict__ err) {
@@ -56,8 +56,7 @@ __global__ void slab_key_kernel(const float4* __restrict__ pos4, uint32_t* __res
     if (k >= n) return;
     float4 p = pos4[k];
     uint32_t cls = slab_class(p.x, g, err);
-    uint32_t t = min(__float_as_uint(p.w), (uint32_t)(c.T - 1));
-    uint32_t key = cf_cell_key(p, c) * (uint32_t)c.T + t; // leavers: clamped cell, irrelevant
+    uint32_t key = cf_sort_key(p, c); // leavers: clamped cell, irrelevant
     keys[k] = cls * g.class_stride + key;
     vals[k] = (uint32_t)k;
 }
@@ -117,8 +116,7 @@ __global__ void slab_unpack_arrivals_kernel(char* __restrict__ msg_from_left, ch
     pos4[n + k] = p;
     vel4[n + k] = mig_vel(msg, cap)[m];
     id[n + k] = mig_id(msg, cap)[m];
-    uint32_t t = min(__float_as_uint(p.w), (uint32_t)(c.T - 1));
-    akeys[k] = cf_cell_key(p, c) * (uint32_t)c.T + t;
+    akeys[k] = cf_sort_key(p, c);
     avals[k] = (uint32_t)(n + k);
 }
 
@@ -188,8 +186,7 @@ __global__ void slab_unpack_ghosts_kernel(char* __restrict__ msg_from_left, char
         pos4[slot] = p;
         id[slot] = halo_id(msg_from_left, cap)[k];
         int cy = cf_cell_coord(p.y, c.inv[1], c.dims[1]), cz = cf_cell_coord(p.z, c.inv[2], c.dims[2]);
-        uint32_t t = min(__float_as_uint(p.w), (uint32_t)(c.T - 1));
-        gkeys_left[k] = (uint32_t)((0 * c.dims[1] + cy) * c.dims[2] + cz) * (uint32_t)c.T + t;
+        gkeys_left[k] = (uint32_t)((0 * c.dims[1] + cy) * c.dims[2] + cz) * CF_KEY_SUB; // cell part only
     }
     if (k < nr) {
         float4 p = halo_pos(msg_from_right, cap)[k];
@@ -197,8 +194,7 @@ __global__ void slab_unpack_ghosts_kernel(char* __restrict__ msg_from_left, char
         pos4[slot] = p;
         id[slot] = halo_id(msg_from_right, cap)[k];
         int cy = cf_cell_coord(p.y, c.inv[1], c.dims[1]), cz = cf_cell_coord(p.z, c.inv[2], c.dims[2]);
-        uint32_t t = min(__float_as_uint(p.w), (uint32_t)(c.T - 1));
-        gkeys_right[k] = (uint32_t)(((c.dims[0] - 1) * c.dims[1] + cy) * c.dims[2] + cz) * (uint32_t)c.T + t;
+        gkeys_right[k] = (uint32_t)(((c.dims[0] - 1) * c.dims[1] + cy) * c.dims[2] + cz) * CF_KEY_SUB;
     }
 }
 
@@ -206,7 +202,7 @@ __global__ void slab_unpack_ghosts_kernel(char* __restrict__ msg_from_left, char
 __global__ void slab_ghost_bounds_kernel(const uint32_t* __restrict__ gkeys_left,
                                          const uint32_t* __restrict__ gkeys_right, char* __restrict__ msg_from_left,
                                          char* __restrict__ msg_from_right, int cap, int* __restrict__ cell_start,
-                                         int layer_cells, int ncell, int own_first, int n_own, int types,
+                                         int layer_cells, int ncell, int own_first, int n_own,
                                          int* __restrict__ ghost_counts) {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     int nl = *halo_count(msg_from_left, cap), nr = *halo_count(msg_from_right, cap);
@@ -215,7 +211,7 @@ __global__ void slab_ghost_bounds_kernel(const uint32_t* __restrict__ gkeys_left
         ghost_counts[1] = nr;
     }
     if (k < layer_cells) { // cells of layer 0: c = k
-        uint32_t want = (uint32_t)k * (uint32_t)types;
+        uint32_t want = (uint32_t)k * CF_KEY_SUB;
         int lo = 0, hi = nl;
         while (lo < hi) {
             int mid = (lo + hi) >> 1;
@@ -224,7 +220,7 @@ __global__ void slab_ghost_bounds_kernel(const uint32_t* __restrict__ gkeys_left
         cell_start[k] = own_first - nl + lo;
     } else if (k < 2 * layer_cells + 1) { // cells of the last layer plus the end sentinel
         int c = ncell - layer_cells + (k - layer_cells);
-        uint32_t want = (uint32_t)c * (uint32_t)types;
+        uint32_t want = (uint32_t)c * CF_KEY_SUB;
         int lo = 0, hi = nr;
         while (lo < hi) {
             int mid = (lo + hi) >> 1;

@@ -99,16 +99,12 @@ __global__ void move_universe_kernel(float4* __restrict__ pos4, int n, float dx,
     pos4[k] = p;
 }
 
-// Sort key + identity permutation (first pass of the cell-list build).  key = cell * T + type:
-// particles of a cell are grouped by type, so the lanes of a warp of the tiled force kernel hold
-// (mostly) one type, i.e. one interaction radius, and accept similar numbers of neighbours.
+// Sort key + identity permutation (first pass of the cell-list build); key = cf_sort_key.
 __global__ void cell_key_kernel(const float4* __restrict__ pos4, uint32_t* __restrict__ keys,
                                 uint32_t* __restrict__ vals, int n, StepConst c) {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
-    float4 p = pos4[k];
-    uint32_t t = min(__float_as_uint(p.w), (uint32_t)(c.T - 1));
-    keys[k] = cf_cell_key(p, c) * (uint32_t)c.T + t;
+    keys[k] = cf_sort_key(pos4[k], c);
     vals[k] = (uint32_t)k;
 }
 
@@ -125,14 +121,14 @@ __global__ void reorder_kernel(const uint32_t* __restrict__ perm, const float4* 
     id_out[s] = id_in[src];
 }
 
-// cellStart[c] = first slot whose key is >= c*T (lower bound over the sorted keys), c in [0, ncell];
+// cellStart[c] = first slot whose key is >= c*64 (lower bound over the sorted keys), c in [0, ncell];
 // cell c occupies slots [cellStart[c], cellStart[c+1]).  One thread per cell, log2(n) probes of an
 // L2-resident array; no worst case for clustered states (unlike a per-particle gap fill).
 __global__ void cell_bounds_kernel(const uint32_t* __restrict__ skeys, int n, int* __restrict__ cell_start,
-                                   int ncell, int base, int types) {
+                                   int ncell, int base) {
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c > ncell) return;
-    const uint32_t want = (uint32_t)c * (uint32_t)types; // first key of cell c
+    const uint32_t want = (uint32_t)c * CF_KEY_SUB; // first key of cell c
     int lo = 0, hi = n;
     while (lo < hi) {
         int mid = (lo + hi) >> 1;

@@ -28,10 +28,9 @@
 #include "cf_device.cuh"
 #include "kernels_force.cuh"
 
+#define TK_IPT 4               // i particles per lane (register tile)
+#define TK_TI (32 * TK_IPT)    // i particles per tile (one warp)
 #define TK_THREADS 128
-#define TK_IPT 4
-#define TK_TI (TK_THREADS * TK_IPT)
-#define TK_JC 128   // j particles per staged chunk
 #define TK_MAX_RUNS 18
 #define TK_FAR 1.0e30f
 
@@ -120,318 +119,305 @@ __global__ void build_tiles_kernel(const int* __restrict__ cell_start, int ncell
     for (int k = 0; k < nt; k++) tiles[base + k] = make_int2(cell, k);
 }
 
-// One 32-j word of the test phase for K i-particles per lane: 8 quads of staged j, each loaded
-// once (3 LDS.128) and tested against all K register-resident i in packed pairs -> K x 32 bits.
-template <int K, bool WRAP, bool UNIFORM>
-__device__ __forceinline__ void tk_test_word(const float* __restrict__ xq, const float* __restrict__ yq,
-                                             const float* __restrict__ zq, const float* __restrict__ hq,
-                                             const u64 (&npx)[TK_IPT], const u64 (&npy)[TK_IPT],
-                                             const u64 (&npz)[TK_IPT], const u64 (&hi2)[TK_IPT], u64 sx,
-                                             u64 sy, u64 sz, float cut, unsigned (&m)[TK_IPT]) {
-#pragma unroll
-    for (int q = 0; q < 8; q++) {
-        const float4 X = *reinterpret_cast<const float4*>(xq + 4 * q);
-        const float4 Y = *reinterpret_cast<const float4*>(yq + 4 * q);
-        const float4 Z = *reinterpret_cast<const float4*>(zq + 4 * q);
-        u64 xa = tk_pack(X.x, X.y), xb = tk_pack(X.z, X.w);
-        u64 ya = tk_pack(Y.x, Y.y), yb = tk_pack(Y.z, Y.w);
-        u64 za = tk_pack(Z.x, Z.y), zb = tk_pack(Z.z, Z.w);
-        u64 ha = 0, hb = 0;
-        if (!UNIFORM) {
-            const float4 H = *reinterpret_cast<const float4*>(hq + 4 * q);
-            ha = tk_pack(H.x, H.y), hb = tk_pack(H.z, H.w);
-        }
-        if (WRAP) { // shift the j side once per quad: (jx + s) is NOT what the reference rounds,
-                    // so the shift is applied after the subtraction below, per k
-        }
+// ---------------------------------------------------------------------------------------------
+// Warp-per-tile pair-force kernel.
+//
+// A warp owns one tile (<= 128 particles of one cell: 4 register-resident "layers" of 32) and
+// streams the neighbour runs through its private double-buffered shared-memory stage, 64 j per
+// chunk; there is no block-level barrier anywhere, so every resident warp always has work
+// whatever the cell occupancy (profiles/r01: a CTA-per-cell version spent 72% of its stall
+// samples at __syncthreads).
+//
+// Inner loop, per quad of 4 staged j (3 broadcast LDS.128) and per layer k:
+//   packed displacement + squared distance for the 4 pairs (12 FADD2/FMUL2/FFMA2),
+//   4 compares, ONE warp vote: if no lane of the layer accepts any of the 4 j the quad is done;
+//   otherwise the force terms of the 4 pairs are evaluated for all lanes from the displacements
+//   still in registers (rejected pairs contribute an exact 0).  Particles are Morton-ordered inside
+//   cells, so a layer and a quad are compact blobs and most quads are decided for the whole warp
+//   at once: no accept masks, no per-lane drain loop, no gathers.
+// ---------------------------------------------------------------------------------------------
+#define TKW_WARPS 4            // warps per CTA (independent of each other)
+#define TKW_JC 64              // staged j per chunk and warp
+
+template <bool UNIFORM>
+struct TkwShared {
+    float x[TKW_WARPS][2][TKW_JC];
+    float y[TKW_WARPS][2][TKW_JC];
+    float z[TKW_WARPS][2][TKW_JC];
+    float h[TKW_WARPS][2][TKW_JC];      // conservative half radius of j (non-uniform radii only)
+    int t[TKW_WARPS][2][TKW_JC];        // byte offset of j's row in the transposed pair table
+};
+
+// Force terms of one packed pair of j against one i (lane).  d* are the packed displacements,
+// d2 the packed squared distances, acc* packed partial sums (lo/hi are added at the end).
+template <bool UNIFORM>
+__device__ __forceinline__ void tkw_force_pair(u64 dx, u64 dy, u64 dz, u64 d2, bool ok0, bool ok1,
+                                               const char* tab_i, int t0, int t1, float c2u, float bu,
+                                               float repulsion, float attraction, float nk_log2e,
+                                               u64& ax, u64& ay, u64& az, int& cnt) {
+    float x0, x1;
+    tk_unpack(tk_add2(d2, tk_pack(0.0001f, 0.0001f)), x0, x1);
+    float s0, s1;
+    if (UNIFORM) {
+        // s = fv * (rep * e / dist - att / Reff), e = exp2(c2 * x)
+        float fv0 = *reinterpret_cast<const float*>(tab_i + t0);
+        float fv1 = *reinterpret_cast<const float*>(tab_i + t1);
+        float r0 = cf_rsqrt(x0), r1 = cf_rsqrt(x1);
+        float e0 = cf_ex2(x0 * c2u), e1 = cf_ex2(x1 * c2u);
+        s0 = fv0 * fmaf(e0 * r0, repulsion, -bu);
+        s1 = fv1 * fmaf(e1 * r1, repulsion, -bu);
+    } else {
+        // table entry = (fv, 1/Reff, cut2, -): the exact accept test happens here
+        float4 p0 = *reinterpret_cast<const float4*>(tab_i + t0);
+        float4 p1 = *reinterpret_cast<const float4*>(tab_i + t1);
+        float a0, a1;
+        tk_unpack(d2, a0, a1);
+        ok0 = a0 < p0.z;
+        ok1 = a1 < p1.z;
+        float r0 = cf_rsqrt(x0), r1 = cf_rsqrt(x1);
+        float e0 = cf_ex2(x0 * (nk_log2e * p0.y * p0.y)), e1 = cf_ex2(x1 * (nk_log2e * p1.y * p1.y));
+        s0 = p0.x * fmaf(e0 * r0, repulsion, -(attraction * p0.y));
+        s1 = p1.x * fmaf(e1 * r1, repulsion, -(attraction * p1.y));
+    }
+    s0 = ok0 ? s0 : 0.f;
+    s1 = ok1 ? s1 : 0.f;
+    cnt += (ok0 ? 1 : 0) + (ok1 ? 1 : 0);
+    u64 s = tk_pack(s0, s1);
+    ax = tk_fma2(s, dx, ax);
+    ay = tk_fma2(s, dy, ay);
+    az = tk_fma2(s, dz, az);
+}
+
+template <bool UNIFORM, bool WRAP, int K>
+__device__ __forceinline__ void tkw_chunk(const float* __restrict__ xs, const float* __restrict__ ys,
+                                          const float* __restrict__ zs, const float* __restrict__ hs,
+                                          const int* __restrict__ ts, int nquads, const float (&npx)[TK_IPT],
+                                          const float (&npy)[TK_IPT], const float (&npz)[TK_IPT],
+                                          const float (&hi)[TK_IPT], const char* const (&tab_i)[TK_IPT],
+                                          float sx, float sy, float sz, float cut, float c2u, float bu,
+                                          const StepConst& c, u64 (&ax)[TK_IPT], u64 (&ay)[TK_IPT],
+                                          u64 (&az)[TK_IPT], int (&cnt)[TK_IPT]) {
+    const u64 sx2 = tk_pack(sx, sx), sy2 = tk_pack(sy, sy), sz2 = tk_pack(sz, sz);
+#pragma unroll 1
+    for (int q = 0; q < nquads; q++) {
+        const float4 X = *reinterpret_cast<const float4*>(xs + 4 * q);
+        const float4 Y = *reinterpret_cast<const float4*>(ys + 4 * q);
+        const float4 Z = *reinterpret_cast<const float4*>(zs + 4 * q);
+        const int4 Tq = *reinterpret_cast<const int4*>(ts + 4 * q);
+        float4 H = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (!UNIFORM) H = *reinterpret_cast<const float4*>(hs + 4 * q);
+        const u64 xa = tk_pack(X.x, X.y), xb = tk_pack(X.z, X.w);
+        const u64 ya = tk_pack(Y.x, Y.y), yb = tk_pack(Y.z, Y.w);
+        const u64 za = tk_pack(Z.x, Z.y), zb = tk_pack(Z.z, Z.w);
 #pragma unroll
         for (int k = 0; k < K; k++) {
-            u64 dxa = tk_add2(xa, npx[k]), dxb = tk_add2(xb, npx[k]);
-            u64 dya = tk_add2(ya, npy[k]), dyb = tk_add2(yb, npy[k]);
-            u64 dza = tk_add2(za, npz[k]), dzb = tk_add2(zb, npz[k]);
+            const u64 px = tk_pack(npx[k], npx[k]), py = tk_pack(npy[k], npy[k]), pz = tk_pack(npz[k], npz[k]);
+            u64 dxa = tk_add2(xa, px), dxb = tk_add2(xb, px);
+            u64 dya = tk_add2(ya, py), dyb = tk_add2(yb, py);
+            u64 dza = tk_add2(za, pz), dzb = tk_add2(zb, pz);
             if (WRAP) {
-                dxa = tk_add2(dxa, sx), dxb = tk_add2(dxb, sx);
-                dya = tk_add2(dya, sy), dyb = tk_add2(dyb, sy);
-                dza = tk_add2(dza, sz), dzb = tk_add2(dzb, sz);
+                dxa = tk_add2(dxa, sx2), dxb = tk_add2(dxb, sx2);
+                dya = tk_add2(dya, sy2), dyb = tk_add2(dyb, sy2);
+                dza = tk_add2(dza, sz2), dzb = tk_add2(dzb, sz2);
             }
-            u64 d2a = tk_fma2(dza, dza, tk_fma2(dxa, dxa, tk_mul2(dya, dya)));
-            u64 d2b = tk_fma2(dzb, dzb, tk_fma2(dxb, dxb, tk_mul2(dyb, dyb)));
+            const u64 d2a = tk_fma2(dza, dza, tk_fma2(dxa, dxa, tk_mul2(dya, dya)));
+            const u64 d2b = tk_fma2(dzb, dzb, tk_fma2(dxb, dxb, tk_mul2(dyb, dyb)));
             float a0, a1, b0, b1;
             tk_unpack(d2a, a0, a1);
             tk_unpack(d2b, b0, b1);
-            float t0 = cut, t1 = cut, t2 = cut, t3 = cut;
-            if (!UNIFORM) {
-                // conservative per-pair bound (h_i + h_j)^2 >= cut2[ti][tj]; exact test in the force phase
-                u64 ta = tk_add2(ha, hi2[k]), tb = tk_add2(hb, hi2[k]);
-                ta = tk_mul2(ta, ta), tb = tk_mul2(tb, tb);
-                tk_unpack(ta, t0, t1);
-                tk_unpack(tb, t2, t3);
+            bool o0, o1, o2, o3;
+            if (UNIFORM) {
+                o0 = a0 < cut, o1 = a1 < cut, o2 = b0 < cut, o3 = b1 < cut;
+            } else { // conservative bound (h_i + h_j)^2 >= cut2[ti][tj]; exact test in the force path
+                float t0 = H.x + hi[k], t1 = H.y + hi[k], t2 = H.z + hi[k], t3 = H.w + hi[k];
+                o0 = a0 < t0 * t0, o1 = a1 < t1 * t1, o2 = b0 < t2 * t2, o3 = b1 < t3 * t3;
             }
-            unsigned mk = m[k];
-            if (a0 < t0) mk |= 1u << (4 * q);
-            if (a1 < t1) mk |= 1u << (4 * q + 1);
-            if (b0 < t2) mk |= 1u << (4 * q + 2);
-            if (b1 < t3) mk |= 1u << (4 * q + 3);
-            m[k] = mk;
+            if (__any_sync(0xffffffffu, o0 || o1 || o2 || o3)) {
+                tkw_force_pair<UNIFORM>(dxa, dya, dza, d2a, o0, o1, tab_i[k], Tq.x, Tq.y, c2u, bu, c.repulsion,
+                                        c.attraction, c.nk_log2e, ax[k], ay[k], az[k], cnt[k]);
+                tkw_force_pair<UNIFORM>(dxb, dyb, dzb, d2b, o2, o3, tab_i[k], Tq.z, Tq.w, c2u, bu, c.repulsion,
+                                        c.attraction, c.nk_log2e, ax[k], ay[k], az[k], cnt[k]);
+            }
         }
-    }
-}
-
-// Test phase of one 64-j block for K i-layers: fills mask[k] (bit b = staged j o + b).
-template <int K, bool UNIFORM>
-__device__ __forceinline__ void tk_test_block(const float* xs, const float* ys, const float* zs, const float* hs,
-                                              int nwords, bool wrap, const u64 (&npx)[TK_IPT],
-                                              const u64 (&npy)[TK_IPT], const u64 (&npz)[TK_IPT],
-                                              const u64 (&hi2)[TK_IPT], u64 sx, u64 sy, u64 sz, float cut,
-                                              u64 (&mask)[TK_IPT]) {
-#pragma unroll
-    for (int k = 0; k < TK_IPT; k++) mask[k] = 0ull;
-#pragma unroll 1
-    for (int w = 0; w < nwords; w++) {
-        unsigned m[TK_IPT];
-#pragma unroll
-        for (int k = 0; k < TK_IPT; k++) m[k] = 0u;
-        const int o = 32 * w;
-        if (wrap)
-            tk_test_word<K, true, UNIFORM>(xs + o, ys + o, zs + o, hs + o, npx, npy, npz, hi2, sx, sy, sz, cut, m);
-        else
-            tk_test_word<K, false, UNIFORM>(xs + o, ys + o, zs + o, hs + o, npx, npy, npz, hi2, sx, sy, sz, cut, m);
-#pragma unroll
-        for (int k = 0; k < K; k++) mask[k] |= (u64)m[k] << o;
     }
 }
 
 template <bool UNIFORM>
-__global__ void __launch_bounds__(TK_THREADS, 4)
+__global__ void __launch_bounds__(TKW_WARPS * 32, 4)
 force_tile_kernel(const float4* __restrict__ pos4, const int* __restrict__ cell_start,
                   const int2* __restrict__ tiles, int* __restrict__ ctrl, float4* __restrict__ frc4,
                   StepConst c, const DeviceTables* __restrict__ tables, float radius_half_scale,
                   const float* __restrict__ half_radius) {
-    __shared__ __align__(16) float s_x[2][TK_JC];
-    __shared__ __align__(16) float s_y[2][TK_JC];
-    __shared__ __align__(16) float s_z[2][TK_JC];
-    __shared__ __align__(16) float s_h[2][TK_JC];
-    __shared__ uint32_t s_t[2][TK_JC];
-    __shared__ TilePairConst s_pc[CF_TT_MAX];
+    __shared__ __align__(16) TkwShared<UNIFORM> sm;
+    // transposed pair table: entry (tj, ti) so that lanes (different ti) read neighbouring words
+    __shared__ __align__(16) float s_tab[CF_TT_MAX * (UNIFORM ? 1 : 4)];
     __shared__ float s_half[CF_T_MAX];
-    __shared__ TileRun s_runs[TK_MAX_RUNS];
-    __shared__ int s_tile;
-
+    (void)radius_half_scale;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int T = c.T;
-    for (int i = tid; i < T * T; i += TK_THREADS) {
-        float inv = tables->inv_reff[i];
-        TilePairConst pc;
-        pc.A = c.repulsion * tables->force[i];
-        pc.B = c.attraction * tables->force[i] * inv;
-        pc.c2 = c.nk_log2e * inv * inv;
-        pc.cut2 = tables->cut2[i];
-        s_pc[i] = pc;
+    for (int i = tid; i < T * T; i += blockDim.x) {
+        int ti = i / T, tj = i % T; // tables are [ti][tj]
+        if (UNIFORM) {
+            s_tab[tj * T + ti] = tables->force[i];
+        } else {
+            float* e = &s_tab[(tj * T + ti) * 4];
+            e[0] = tables->force[i];
+            e[1] = tables->inv_reff[i];
+            e[2] = tables->cut2[i];
+            e[3] = 0.f;
+        }
     }
     if (tid < T) s_half[tid] = half_radius[tid];
-    (void)radius_half_scale;
+    __syncthreads(); // the only block-level barrier: tables are read-only afterwards
+    const int entry = UNIFORM ? 4 : 16;       // bytes per table entry
+    const int row_bytes = T * entry;          // one tj row
     const int ntiles = ctrl[0];
     const int ny = c.dims[1], nz = c.dims[2];
+    const float cut = c.cut2_uniform;
+    const float c2u = c.nk_log2e * c.inv_reff_uniform * c.inv_reff_uniform;
+    const float bu = c.attraction * c.inv_reff_uniform;
+    float* const wx = &sm.x[warp][0][0];
+    float* const wy = &sm.y[warp][0][0];
+    float* const wz = &sm.z[warp][0][0];
+    float* const wh = &sm.h[warp][0][0];
+    int* const wt = &sm.t[warp][0][0];
 
     for (;;) {
-        __syncthreads(); // previous tile fully done (smem reuse), tables visible
-        if (tid == 0) s_tile = atomicAdd(&ctrl[1], 1);
-        __syncthreads();
-        const int tile = s_tile;
+        int tile = 0;
+        if (lane == 0) tile = atomicAdd(&ctrl[1], 1);
+        tile = __shfl_sync(0xffffffffu, tile, 0);
         if (tile >= ntiles) break;
         const int2 tl = tiles[tile];
         const int cell = tl.x;
         const int cz = cell % nz, cy = (cell / nz) % ny, cx = cell / (nz * ny);
         const int i_begin = cell_start[cell] + tl.y * TK_TI;
-        const int i_end = min(cell_start[cell + 1], i_begin + TK_TI);
-        const int ni = i_end - i_begin;
+        const int ni = min(cell_start[cell + 1] - i_begin, TK_TI);
 
-        // ---- neighbour runs: 9 (x, y) rows x {main z segment, wrapped z segment} ----------
-        if (tid < TK_MAX_RUNS) {
-            int rho = tid >> 1, seg = tid & 1;
-            int ddx = rho / 3 - 1, ddy = rho % 3 - 1;
-            int x = cx + ddx, y = cy + ddy;
-            float sx = 0.f, sy = 0.f, sz = 0.f;
+        // ---- neighbour runs: lane r < 18 holds run r = (row r/2 of the 3x3 (x,y) rows, z segment r%2)
+        int r_j0 = 0, r_j1 = 0;
+        float r_sx = 0.f, r_sy = 0.f, r_sz = 0.f;
+        if (lane < TK_MAX_RUNS) {
+            int rho = lane >> 1, seg = lane & 1;
+            int x = cx + rho / 3 - 1, y = cy + rho % 3 - 1;
             bool valid = true;
             if (c.periodic_x) {
-                if (x < 0) { x = c.dims[0] - 1; sx = -c.W[0]; } else if (x >= c.dims[0]) { x = 0; sx = c.W[0]; }
+                if (x < 0) { x = c.dims[0] - 1; r_sx = -c.W[0]; } else if (x >= c.dims[0]) { x = 0; r_sx = c.W[0]; }
             } else { // slab mode: i-cells are layers 1..dims-2, so x stays inside [0, dims-1]
                 if (x < 0 || x >= c.dims[0]) valid = false;
-                else if (x == 0) sx = c.gshift_lo;
-                else if (x == c.dims[0] - 1) sx = c.gshift_hi;
+                else if (x == 0) r_sx = c.gshift_lo;
+                else if (x == c.dims[0] - 1) r_sx = c.gshift_hi;
             }
-            if (y < 0) { y = ny - 1; sy = -c.W[1]; } else if (y >= ny) { y = 0; sy = c.W[1]; }
-            int z0, z1;
+            if (y < 0) { y = ny - 1; r_sy = -c.W[1]; } else if (y >= ny) { y = 0; r_sy = c.W[1]; }
+            int z0 = 0, z1 = 0;
             if (seg == 0) {
                 z0 = max(cz - 1, 0);
                 z1 = min(cz + 1, nz - 1);
             } else if (cz == 0) {
                 z0 = z1 = nz - 1;
-                sz = -c.W[2];
+                r_sz = -c.W[2];
             } else if (cz == nz - 1) {
                 z0 = z1 = 0;
-                sz = c.W[2];
+                r_sz = c.W[2];
             } else {
                 valid = false;
-                z0 = z1 = 0;
             }
-            TileRun r;
-            r.j0 = r.j1 = 0;
             if (valid) {
                 int row = (x * ny + y) * nz;
-                r.j0 = cell_start[row + z0];
-                r.j1 = cell_start[row + z1 + 1];
+                r_j0 = cell_start[row + z0];
+                r_j1 = cell_start[row + z1 + 1];
             }
-            r.sx = sx, r.sy = sy, r.sz = sz;
-            r.wrap = (sx != 0.f || sy != 0.f || sz != 0.f) ? 1 : 0;
-            s_runs[tid] = r;
         }
 
-        // ---- my i particles: slot = i_begin + warp*128 + k*32 + lane (fills whole warps first) ----
-        u64 npx[TK_IPT], npy[TK_IPT], npz[TK_IPT], hi2[TK_IPT];
-        float fx[TK_IPT], fy[TK_IPT], fz[TK_IPT];
-        const float cut = c.cut2_uniform;
-        int cnt[TK_IPT], ti[TK_IPT];
-        const int warp_first = warp * (32 * TK_IPT);
-        int kmax = 0; // i-layers this warp actually holds (warp-uniform)
+        // ---- my i particles: layer k holds slots i_begin + 32k + lane ----
+        float npx[TK_IPT], npy[TK_IPT], npz[TK_IPT], hi[TK_IPT];
+        const char* tab_i[TK_IPT];
+        u64 ax[TK_IPT], ay[TK_IPT], az[TK_IPT];
+        int cnt[TK_IPT], self_ok[TK_IPT];
+        const int kmax = (ni + 31) >> 5;
 #pragma unroll
         for (int k = 0; k < TK_IPT; k++) {
-            int il = warp_first + k * 32 + lane;
+            int il = k * 32 + lane;
             bool v = il < ni;
             float4 p = v ? pos4[i_begin + il] : make_float4(-TK_FAR, -TK_FAR, -TK_FAR, 0.f);
-            ti[k] = v ? (int)__float_as_uint(p.w) : 0;
-            npx[k] = tk_pack(-p.x, -p.x);
-            npy[k] = tk_pack(-p.y, -p.y);
-            npz[k] = tk_pack(-p.z, -p.z);
-            float h = v ? s_half[ti[k]] : 0.f;
-            hi2[k] = tk_pack(h, h);
-            fx[k] = fy[k] = fz[k] = 0.f;
+            int ti = v ? (int)__float_as_uint(p.w) : 0;
+            npx[k] = -p.x, npy[k] = -p.y, npz[k] = -p.z;
+            hi[k] = v ? s_half[ti] : 0.f;
+            tab_i[k] = reinterpret_cast<const char*>(s_tab) + ti * entry;
+            ax[k] = ay[k] = az[k] = tk_pack(0.f, 0.f);
             cnt[k] = 0;
-            if (warp_first + k * 32 < ni) kmax = k + 1;
+            self_ok[k] = (UNIFORM ? cut : s_tab[(ti * T + ti) * 4 + 2]) > 0.f ? 1 : 0;
         }
-        __syncthreads(); // runs visible (s_half was synced before the loop's first barrier)
 
-        // ---- chunk stream over the runs, double-buffered ------------------------------------
-        int run = 0, off = 0;
-        // advance to the first non-empty run
-        while (run < TK_MAX_RUNS && s_runs[run].j1 - s_runs[run].j0 <= 0) run++;
-        // stage the first chunk
-        auto stage = [&](int buf, int r, int o) {
-            int j = s_runs[r].j0 + o + tid;
-            bool v = j < s_runs[r].j1;
-            float4 q = v ? pos4[j] : make_float4(TK_FAR, TK_FAR, TK_FAR, 0.f);
-            s_x[buf][tid] = q.x;
-            s_y[buf][tid] = q.y;
-            s_z[buf][tid] = q.z;
-            uint32_t tj = v ? __float_as_uint(q.w) : 0u;
-            s_t[buf][tid] = tj;
-            if (!UNIFORM) s_h[buf][tid] = v ? s_half[tj] : 0.f;
-        };
+        // ---- stream the runs ----
         int buf = 0;
-        if (run < TK_MAX_RUNS) stage(0, run, 0);
-        __syncthreads();
-        while (run < TK_MAX_RUNS) {
-            const TileRun R = s_runs[run];
-            const int cntj = min(TK_JC, R.j1 - R.j0 - off);
-            // next chunk coordinates (uniform)
-            int nrun = run, noff = off + TK_JC;
-            if (noff >= R.j1 - R.j0) {
-                nrun = run + 1;
-                noff = 0;
-                while (nrun < TK_MAX_RUNS && s_runs[nrun].j1 - s_runs[nrun].j0 <= 0) nrun++;
-            }
-            // prefetch the next chunk's particle into registers (latency hidden by the compute)
-            float4 nq = make_float4(TK_FAR, TK_FAR, TK_FAR, 0.f);
-            bool nv = false;
-            if (nrun < TK_MAX_RUNS) {
-                int j = s_runs[nrun].j0 + noff + tid;
-                nv = j < s_runs[nrun].j1;
-                if (nv) nq = pos4[j];
-            }
-
-            if (kmax > 0) {
-                const u64 sx2 = tk_pack(R.sx, R.sx), sy2 = tk_pack(R.sy, R.sy), sz2 = tk_pack(R.sz, R.sz);
-                const int nblk = (cntj + 63) >> 6; // 64-j blocks in this chunk
-                for (int blk = 0; blk < nblk; blk++) {
-                    const int o = blk * 64;
-                    u64 mask[TK_IPT];
-                    // ---------------- test phase ----------------
-                    const int nwords = cntj > o + 32 ? 2 : 1;
-                    const float* xs = &s_x[buf][o];
-                    const float* ys = &s_y[buf][o];
-                    const float* zs = &s_z[buf][o];
-                    const float* hs = &s_h[buf][o];
-                    switch (kmax) { // warp-uniform
-                        case 1: tk_test_block<1, UNIFORM>(xs, ys, zs, hs, nwords, R.wrap != 0, npx, npy, npz, hi2, sx2, sy2, sz2, cut, mask); break;
-                        case 2: tk_test_block<2, UNIFORM>(xs, ys, zs, hs, nwords, R.wrap != 0, npx, npy, npz, hi2, sx2, sy2, sz2, cut, mask); break;
-                        case 3: tk_test_block<3, UNIFORM>(xs, ys, zs, hs, nwords, R.wrap != 0, npx, npy, npz, hi2, sx2, sy2, sz2, cut, mask); break;
-                        default: tk_test_block<4, UNIFORM>(xs, ys, zs, hs, nwords, R.wrap != 0, npx, npy, npz, hi2, sx2, sy2, sz2, cut, mask); break;
-                    }
-                    if (UNIFORM) {
-#pragma unroll
-                        for (int k = 0; k < TK_IPT; k++) cnt[k] += __popcll(mask[k]);
-                    }
-                    // ---------------- force phase: set bits only ----------------
-#pragma unroll
-                    for (int k = 0; k < TK_IPT; k++) {
-                        if (k < kmax) {
-                            u64 m = mask[k];
-                            float px, py, pz, dummy;
-                            tk_unpack(npx[k], px, dummy);
-                            tk_unpack(npy[k], py, dummy);
-                            tk_unpack(npz[k], pz, dummy);
-                            const TilePairConst* row = &s_pc[ti[k] * T];
-                            while (__any_sync(0xffffffffu, m != 0ull)) {
-                                if (m != 0ull) {
-                                    int b = __ffsll((long long)m) - 1;
-                                    m &= m - 1ull;
-                                    int j = o + b;
-                                    float dx = __fadd_rn(__fadd_rn(s_x[buf][j], px), R.sx);
-                                    float dy = __fadd_rn(__fadd_rn(s_y[buf][j], py), R.sy);
-                                    float dz = __fadd_rn(__fadd_rn(s_z[buf][j], pz), R.sz);
-                                    float d2 = cf_dist2(dx, dy, dz);
-                                    TilePairConst pc = row[s_t[buf][j]];
-                                    bool ok = UNIFORM ? true : (d2 < pc.cut2);
-                                    if (ok) {
-                                        if (!UNIFORM) cnt[k]++;
-                                        float x = __fadd_rn(d2, 0.0001f);
-                                        float rinv = cf_rsqrt(x);
-                                        float e = cf_ex2(x * pc.c2);
-                                        float s = fmaf(e * pc.A, rinv, -pc.B);
-                                        fx[k] = fmaf(s, dx, fx[k]);
-                                        fy[k] = fmaf(s, dy, fy[k]);
-                                        fz[k] = fmaf(s, dz, fz[k]);
-                                    }
-                                }
-                            }
-                        }
+        for (int r = 0; r < TK_MAX_RUNS; r++) {
+            const int j0 = __shfl_sync(0xffffffffu, r_j0, r), j1 = __shfl_sync(0xffffffffu, r_j1, r);
+            if (j1 <= j0) continue;
+            const float sx = __shfl_sync(0xffffffffu, r_sx, r), sy = __shfl_sync(0xffffffffu, r_sy, r),
+                        sz = __shfl_sync(0xffffffffu, r_sz, r);
+            const bool wrap = (sx != 0.f) || (sy != 0.f) || (sz != 0.f);
+            // prefetch the first chunk of the run
+            float4 q0 = make_float4(TK_FAR, TK_FAR, TK_FAR, 0.f), q1 = q0;
+            if (j0 + lane < j1) q0 = pos4[j0 + lane];
+            if (j0 + 32 + lane < j1) q1 = pos4[j0 + 32 + lane];
+            for (int off = j0; off < j1; off += TKW_JC) {
+                // publish the prefetched chunk
+                float* bx = wx + buf * TKW_JC;
+                float* by = wy + buf * TKW_JC;
+                float* bz = wz + buf * TKW_JC;
+                float* bh = wh + buf * TKW_JC;
+                int* bt = wt + buf * TKW_JC;
+                {
+                    int t0 = (int)__float_as_uint(q0.w), t1 = (int)__float_as_uint(q1.w);
+                    bx[lane] = q0.x, by[lane] = q0.y, bz[lane] = q0.z, bt[lane] = t0 * row_bytes;
+                    bx[lane + 32] = q1.x, by[lane + 32] = q1.y, bz[lane + 32] = q1.z, bt[lane + 32] = t1 * row_bytes;
+                    if (!UNIFORM) {
+                        bh[lane] = off + lane < j1 ? s_half[t0] : 0.f;
+                        bh[lane + 32] = off + 32 + lane < j1 ? s_half[t1] : 0.f;
                     }
                 }
+                __syncwarp();
+                const int cntj = min(TKW_JC, j1 - off);
+                // prefetch the next chunk while this one is processed
+                const int noff = off + TKW_JC;
+                q0 = make_float4(TK_FAR, TK_FAR, TK_FAR, 0.f);
+                q1 = q0;
+                if (noff + lane < j1) q0 = pos4[noff + lane];
+                if (noff + 32 + lane < j1) q1 = pos4[noff + 32 + lane];
+                const int nquads = (cntj + 3) >> 2;
+#define TKW_CALL(WR, KK)                                                                                  \
+    tkw_chunk<UNIFORM, WR, KK>(bx, by, bz, bh, bt, nquads, npx, npy, npz, hi, tab_i, sx, sy, sz, cut, c2u, bu, \
+                               c, ax, ay, az, cnt)
+                if (wrap) {
+                    switch (kmax) {
+                        case 1: TKW_CALL(true, 1); break;
+                        case 2: TKW_CALL(true, 2); break;
+                        case 3: TKW_CALL(true, 3); break;
+                        default: TKW_CALL(true, 4); break;
+                    }
+                } else {
+                    switch (kmax) {
+                        case 1: TKW_CALL(false, 1); break;
+                        case 2: TKW_CALL(false, 2); break;
+                        case 3: TKW_CALL(false, 3); break;
+                        default: TKW_CALL(false, 4); break;
+                    }
+                }
+#undef TKW_CALL
+                buf ^= 1; // the other buffer was last read one chunk ago by this same warp
             }
-
-            // publish the prefetched chunk into the other buffer
-            if (nrun < TK_MAX_RUNS) {
-                int nb = buf ^ 1;
-                s_x[nb][tid] = nq.x;
-                s_y[nb][tid] = nq.y;
-                s_z[nb][tid] = nq.z;
-                uint32_t tj = nv ? __float_as_uint(nq.w) : 0u;
-                s_t[nb][tid] = tj;
-                if (!UNIFORM) s_h[nb][tid] = nv ? s_half[tj] : 0.f;
-            }
-            __syncthreads();
-            buf ^= 1;
-            run = nrun;
-            off = noff;
         }
 
         // ---- write back: the particle itself was tested too (d = 0, force term exactly 0) ----
 #pragma unroll
         for (int k = 0; k < TK_IPT; k++) {
-            int il = warp_first + k * 32 + lane;
+            int il = k * 32 + lane;
             if (il < ni) {
-                int self = s_pc[ti[k] * T + ti[k]].cut2 > 0.f ? 1 : 0;
-                frc4[i_begin + il] = make_float4(fx[k], fy[k], fz[k], __int_as_float(cnt[k] - self));
+                float x0, x1, y0, y1, z0, z1;
+                tk_unpack(ax[k], x0, x1);
+                tk_unpack(ay[k], y0, y1);
+                tk_unpack(az[k], z0, z1);
+                frc4[i_begin + il] = make_float4(x0 + x1, y0 + y1, z0 + z1, __int_as_float(cnt[k] - self_ok[k]));
             }
         }
     }

@@ -150,7 +150,7 @@ static int ensure_sorted_slab(cf_sim* s, cudaEvent_t ev_x0, cudaEvent_t ev_x1) {
     const int cur = s->cur, nxt = cur ^ 1;
     const int B = s->base;
     int n = s->n;
-    const long long KC = (long long)s->ncell * s->T;
+    const long long KC = (long long)s->ncell * CF_KEY_SUB;
     s->geom.class_stride = (uint32_t)KC;
     int src = 0;
     int n_stay = 0, n_left = 0, n_right = 0;
@@ -204,7 +204,7 @@ static int ensure_sorted_slab(cf_sim* s, cudaEvent_t ev_x0, cudaEvent_t ev_x1) {
     if (n_new > 0)
         LAUNCH(s, reorder_kernel, div_up(n_new, 256), 256, 0, fvals, s->pos[cur] + B, s->vel[cur] + B, s->id[cur] + B,
                s->pos[nxt] + B, s->vel[nxt] + B, s->id[nxt] + B, n_new);
-    LAUNCH(s, cell_bounds_kernel, div_up(s->ncell + 1, 256), 256, 0, fkeys, n_new, s->cell_start, s->ncell, B, s->T);
+    LAUNCH(s, cell_bounds_kernel, div_up(s->ncell + 1, 256), 256, 0, fkeys, n_new, s->cell_start, s->ncell, B);
     if (src != 0) std::swap(s->keys[0], s->keys[1]), std::swap(s->vals[0], s->vals[1]);
     s->cur = nxt;
     s->n = n_new;
@@ -219,8 +219,7 @@ static int ensure_sorted_slab(cf_sim* s, cudaEvent_t ev_x0, cudaEvent_t ev_x1) {
     LAUNCH(s, slab_unpack_ghosts_kernel, div_up(s->cap_halo, 256), 256, 0, s->recv_halo[0], s->recv_halo[1], s->cap_halo,
            s->pos[nxt], s->id[nxt], B, n_new, s->gkeys[0], s->gkeys[1], s->sc);
     LAUNCH(s, slab_ghost_bounds_kernel, div_up(2 * layer_cells + 1, 256), 256, 0, s->gkeys[0], s->gkeys[1],
-           s->recv_halo[0], s->recv_halo[1], s->cap_halo, s->cell_start, layer_cells, s->ncell, B, n_new, s->T,
-           s->d_slab_counts + 4);
+           s->recv_halo[0], s->recv_halo[1], s->cap_halo, s->cell_start, layer_cells, s->ncell, B, n_new, s->d_slab_counts + 4);
     if (ev_x1) CU(cudaEventRecord(ev_x1, s->stream));
     s->sorted_valid = true;
     CU(cudaGetLastError());

@@ -240,7 +240,7 @@ int cf_download_particles_ids(cf_sim* sim, cf_particle* aos, int32_t* counts, in
 
 int cf_get_stats(cf_sim* sim, cf_stats* stats);
 int cf_stats_reset(cf_sim* sim);
-/* Sorted-order views for the cell-assignment parity tests: sort key (= cell * T + type) and
+/* Sorted-order views for the cell-assignment parity tests: sort key (= cell * 64 + Morton code of the 4x4x4 sub-cell) and
  * original id per slot. */
 int cf_download_cell_keys(cf_sim* sim, uint32_t* keys, int32_t* ids, int capacity, int* count);
 /* Tuning knobs (0 = automatic): stencil half-width m (cell edge = R_max/m rounded to the grid). */

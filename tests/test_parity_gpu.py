@@ -156,13 +156,19 @@ def test_cell_assignment_bit_exact():
     sim = make_sim(p, table, radio, state, counts)
     keys, ids = sim.cellKeys()
     dims = np.int32(list(sim.stats().grid))
-    T = p.numParticleTypes
-    want = O.cell_keys(state, p.canvas, dims) * np.uint32(T) + state["ptype"]   # key = cell*T + type
+    # key = cell*64 + Morton code of the 4x4x4 sub-cell (z bit lowest)
+    inv = dims.astype(np.float32) / p.canvas
+    y = (state["pos"] * inv).astype(np.float32)
+    cell3 = np.minimum(y.astype(np.int32), dims - 1)
+    sub = np.clip(np.minimum((y * np.float32(4)).astype(np.int32), 4 * dims - 1) - 4 * cell3, 0, 3).astype(np.uint32)
+    spread = lambda v: (v & 1) | ((v & 2) << 2)
+    morton = spread(sub[:, 2]) | (spread(sub[:, 1]) << 1) | (spread(sub[:, 0]) << 2)
+    want = O.cell_keys(state, p.canvas, dims) * np.uint32(64) + morton
     assert sorted(ids.tolist()) == list(range(len(state)))          # a permutation
     assert np.array_equal(keys, want[ids])                          # key of every slot
     assert np.all(np.diff(keys.astype(np.int64)) >= 0)              # sorted
     same = keys[1:] == keys[:-1]
-    assert np.all(ids[1:][same] > ids[:-1][same])                   # stable inside a (cell, type)
+    assert np.all(ids[1:][same] > ids[:-1][same])                   # stable inside a sub-cell
     sim.close()
 
 
