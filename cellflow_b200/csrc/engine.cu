@@ -59,6 +59,7 @@ extern "C" const char* cf_version(void) { return "cellflow_b200 0.1 (sm_100a)"; 
 // ---------------------------------------------------------------------------------------------
 struct StepEvents {
     cudaEvent_t e[6]; // begin, after cell list, after force, after integrate, exchange begin/end
+    bool has_exchange = false; // e[4], e[5] were recorded for this step
 };
 
 struct cf_sim {
@@ -99,6 +100,14 @@ struct cf_sim {
     AosParticle* d_aos = nullptr;
     int* d_counts = nullptr;
     unsigned long long* d_accum = nullptr;
+
+    // proximity graph: its own (type, cell) list
+    uint32_t* gk[2] = {nullptr, nullptr};
+    uint32_t* gv[2] = {nullptr, nullptr};
+    float4* gpos = nullptr;
+    size_t graph_cap = 0;
+    int* gstart = nullptr;
+    size_t gstart_cap = 0;
 
     // tile kernel
     int2* d_tiles = nullptr;
@@ -568,6 +577,9 @@ extern "C" int cf_destroy(cf_sim* s) {
     cudaFree(s->d_edge_count);
     cudaFree(s->d_accum);
     cudaFree(s->d_tiles);
+    for (int b = 0; b < 2; b++) cudaFree(s->gk[b]), cudaFree(s->gv[b]);
+    cudaFree(s->gpos);
+    cudaFree(s->gstart);
     cudaFree(s->d_tile_ctrl);
     cudaFree(s->d_half);
     for (auto& ev : s->ev_pool)
@@ -886,6 +898,7 @@ extern "C" int cf_step(cf_sim* s, const cf_params* p, int n_steps) {
     for (int it = 0; it < n_steps; it++) {
         StepEvents* ev = next_events(s);
         if (ev) CU(cudaEventRecord(ev->e[0], s->stream));
+        if (ev) ev->has_exchange = s->slab && !s->sorted_valid;
         if (int rc = build_cell_list(s, ev ? ev->e[4] : nullptr, ev ? ev->e[5] : nullptr)) return rc;
         if (ev) CU(cudaEventRecord(ev->e[1], s->stream));
         if (s->n > 0)
@@ -947,18 +960,76 @@ extern "C" int cf_build_graph(cf_sim* s, float dist, int max_conn, int* n_edges)
     }
     if (s->opt_timing) CU(cudaEventRecord(s->ev_g0, s->stream));
     if (int rc = build_cell_list(s)) return rc;
-    float min_edge = 1e30f;
-    for (int a = 0; a < 3; a++) {
-        float e = a == 0 && s->slab ? (s->sc.W[0] / (float)s->world) / (float)s->nxl : s->sc.W[a] / (float)s->sc.dims[a];
-        min_edge = std::min(min_edge, e);
+    // ---- slots that take part: owned, plus ghost layers that are real neighbours (not the seam) ----
+    int first = s->base, count = s->n;
+    float ext_lo[3] = {0.f, 0.f, 0.f};
+    float ext_hi[3] = {s->sc.W[0], s->sc.W[1], s->sc.W[2]};
+    if (s->slab) {
+        float ex = (s->sc.W[0] / (float)s->world) / (float)s->nxl;
+        if ((double)dist * (1.0 + 1e-5) > (double)ex)
+            return fail(CF_ERR_ARG, "proximity distance %.1f exceeds the one-cell ghost layer (%.1f) of slab mode", dist, ex);
+        int g[2] = {0, 0};
+        CU(cudaMemcpyAsync(g, s->d_slab_counts + 4, 2 * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+        CU(cudaStreamSynchronize(s->stream));
+        if (s->rank > 0) first -= g[0], count += g[0];
+        if (s->rank < s->world - 1) count += g[1];
+        ext_lo[0] = s->geom.x_lo - ex;
+        ext_hi[0] = s->geom.x_hi + ex;
     }
-    int m = (int)ceil((double)dist * (1.0 + 1e-5) / (double)min_edge);
-    m = std::max(m, 1);
-    if (s->slab && m > 1)
-        return fail(CF_ERR_ARG, "proximity distance %.1f exceeds the one-cell ghost layer (%.1f) of slab mode", dist, min_edge);
     CU(cudaMemsetAsync(s->d_edge_count, 0, sizeof(int), s->stream));
-    if (s->n > 0) LAUNCH(s, graph_kernel, div_up(s->n, 128), 128, 0, s->pos[s->cur], s->id[s->cur], s->cell_start, s->base, s->n,
-           s->sc, dist * dist, mc, m, s->edges, s->edge_slots, s->edge_cap, s->d_edge_count);
+    if (count > 0 && s->n > 0) {
+        // ---- the graph's own (type, cell) list, cell edge >= dist ----
+        GraphGrid g;
+        memset(&g, 0, sizeof(g));
+        double edge = (double)dist * (1.0 + 1e-5), vol = 1.0;
+        for (int a = 0; a < 3; a++) vol *= (double)(ext_hi[a] - ext_lo[a]);
+        double max_keys = std::min(4.0 * count + 4096.0, 1.6e7);
+        edge = std::max(edge, cbrt(vol * s->T / max_keys));
+        long long nc = 1;
+        for (int a = 0; a < 3; a++) {
+            int d = (int)floor((double)(ext_hi[a] - ext_lo[a]) / edge);
+            d = std::max(1, std::min(d, 1024));
+            g.dims[a] = d;
+            g.org[a] = ext_lo[a];
+            g.inv[a] = (float)d / (ext_hi[a] - ext_lo[a]);
+            nc *= d;
+        }
+        g.ncell = (int)nc;
+        g.T = s->T;
+        g.x_min = -INFINITY;
+        g.x_max = INFINITY;
+        const int nkeys = s->T * g.ncell; // key nkeys = "not gridded"
+        if ((size_t)count > s->graph_cap) {
+            CU(cudaStreamSynchronize(s->stream));
+            for (int b = 0; b < 2; b++) {
+                cudaFree(s->gk[b]);
+                cudaFree(s->gv[b]);
+                s->gk[b] = s->gv[b] = nullptr;
+            }
+            cudaFree(s->gpos);
+            s->gpos = nullptr;
+            s->graph_cap = (size_t)count + (size_t)count / 8 + 1024;
+            for (int b = 0; b < 2; b++) {
+                CU(cudaMalloc(&s->gk[b], s->graph_cap * sizeof(uint32_t)));
+                CU(cudaMalloc(&s->gv[b], s->graph_cap * sizeof(uint32_t)));
+            }
+            CU(cudaMalloc(&s->gpos, s->graph_cap * sizeof(float4)));
+        }
+        if ((size_t)nkeys + 2 > s->gstart_cap) {
+            CU(cudaStreamSynchronize(s->stream));
+            cudaFree(s->gstart);
+            s->gstart = nullptr;
+            s->gstart_cap = (size_t)nkeys + 2 + (size_t)nkeys / 4;
+            CU(cudaMalloc(&s->gstart, s->gstart_cap * sizeof(int)));
+        }
+        LAUNCH(s, graph_key_kernel, div_up(count, 256), 256, 0, s->pos[s->cur], first, count, g, s->gk[0], s->gv[0]);
+        int src = 0;
+        if (int rc = radix_sort_pairs(s, s->gk, s->gv, count, (long long)nkeys + 1, &src)) return rc;
+        LAUNCH(s, graph_gather_kernel, div_up(count, 256), 256, 0, s->gv[src], s->pos[s->cur], s->id[s->cur], count, s->gpos);
+        LAUNCH(s, graph_bounds_kernel, div_up(nkeys + 1, 256), 256, 0, s->gk[src], count, s->gstart, nkeys);
+        LAUNCH(s, graph_kernel, div_up(count, 128), 128, 0, s->gpos, s->gv[src], s->gk[src], s->gstart, count, s->base,
+               s->n, g, dist * dist, mc, s->edges, s->edge_slots, s->edge_cap, s->d_edge_count);
+    }
     if (s->opt_timing) {
         CU(cudaEventRecord(s->ev_g1, s->stream));
         s->graph_timed = true;
@@ -1065,7 +1136,7 @@ extern "C" int cf_get_stats(cf_sim* s, cf_stats* st) {
         s->ms_sort += a;
         s->ms_force += b;
         s->ms_integrate += c;
-        if (s->slab) {
+        if (ev.has_exchange) {
             float x = 0;
             if (cudaEventElapsedTime(&x, ev.e[4], ev.e[5]) == cudaSuccess) s->ms_exchange += x;
         }

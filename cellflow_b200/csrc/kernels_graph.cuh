@@ -4,80 +4,144 @@
 //   candidates = the first 2*maxConn particles j > i IN ORIGINAL INDEX ORDER with the same type
 //   and plain (non-wrapped) d2 = fma(dz,dz,fma(dx,dx,dy*dy)) < dist^2; stable insertion sort by
 //   d2; keep the first maxConn.
-// The reference scans all j > i; here candidates come from the (2m+1)^3 cells around i (clamped,
-// not periodic, because the rule does not wrap), the 2*maxConn smallest original ids are kept in
-// a sorted per-thread list, and the same stable sort by d2 selects the edges.  The edge SET is
+// The reference scans all j > i; here candidates come from the 27 cells (clamped, not periodic,
+// because the rule does not wrap) of a dedicated (type, cell) list with cell edge >= dist, the
+// 2*maxConn smallest original ids are kept in a sorted per-thread list, and the same stable sort
+// by d2 selects the edges.  The edge SET is
 // identical; the reference's own edge ORDER is nondeterministic (one atomicAdd per thread).
 #pragma once
 #include "cf_device.cuh"
 
 #define CF_GRAPH_K 32 // 2 * CF_MAX_GRAPH_CONN candidates, the reference's nearby[32] (.cu:210)
 
+// The graph has its own cell list: only same-type pairs within `dist` matter, so particles are
+// keyed by (type, cell of edge >= dist) — 27 cells then hold ~27 * n_type * dist^3 / V candidates
+// instead of every particle of 27 force cells of all types (25x fewer at BASELINE config 5).
+struct GraphGrid {
+    float org[3];   // lower corner of the gridded region
+    float inv[3];   // cells per unit length
+    int dims[3];
+    int ncell;      // dims product
+    int T;
+    float x_min, x_max; // particles outside [x_min, x_max) (seam ghosts) are not gridded
+};
+
+__device__ __forceinline__ int graph_coord(float x, float org, float inv, int n) {
+    int c = (int)__fmul_rn(__fsub_rn(x, org), inv);
+    return c < 0 ? 0 : (c > n - 1 ? n - 1 : c);
+}
+
+// key = type * ncell + cell for every slot in [first, first + n); excluded slots get the end key.
+__global__ void graph_key_kernel(const float4* __restrict__ pos4, int first, int n, GraphGrid g,
+                                 uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    float4 p = pos4[first + k];
+    uint32_t t = __float_as_uint(p.w);
+    uint32_t key = (uint32_t)g.T * (uint32_t)g.ncell; // "not gridded"
+    if (t < (uint32_t)g.T && p.x >= g.x_min && p.x < g.x_max) {
+        int cx = graph_coord(p.x, g.org[0], g.inv[0], g.dims[0]);
+        int cy = graph_coord(p.y, g.org[1], g.inv[1], g.dims[1]);
+        int cz = graph_coord(p.z, g.org[2], g.inv[2], g.dims[2]);
+        key = t * (uint32_t)g.ncell + (uint32_t)((cx * g.dims[1] + cy) * g.dims[2] + cz);
+    }
+    keys[k] = key;
+    vals[k] = (uint32_t)(first + k);
+}
+
+// Positions in graph order with the original id in .w, so the candidate loop is one 16-byte load.
+__global__ void graph_gather_kernel(const uint32_t* __restrict__ gvals, const float4* __restrict__ pos4,
+                                    const int* __restrict__ id, int n, float4* __restrict__ gpos) {
+    int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    uint32_t slot = gvals[q];
+    float4 p = pos4[slot];
+    gpos[q] = make_float4(p.x, p.y, p.z, __int_as_float(id[slot]));
+}
+
+// gstart[k] = first graph-order position whose key is >= k, k in [0, nkeys].
+__global__ void graph_bounds_kernel(const uint32_t* __restrict__ skeys, int n, int* __restrict__ gstart, int nkeys) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k > nkeys) return;
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (skeys[mid] < (uint32_t)k) lo = mid + 1; else hi = mid;
+    }
+    gstart[k] = lo;
+}
+
+// One thread per graph-order position q (threads of a warp share a cell: candidate loads are
+// warp-uniform broadcasts).  Only owned particles (slot in [own_first, own_first + n_own)) emit.
 __global__ void __launch_bounds__(128)
-graph_kernel(const float4* __restrict__ pos4, const int* __restrict__ id, const int* __restrict__ cell_start,
-             int first, int n, StepConst c, float dist2, int max_conn, int m, int2* __restrict__ edges,
-             int2* __restrict__ edge_slots, int capacity, int* __restrict__ edge_count) {
-    int s = first + blockIdx.x * blockDim.x + threadIdx.x;
-    bool active = s < first + n;
+graph_kernel(const float4* __restrict__ gpos, const uint32_t* __restrict__ gvals, const uint32_t* __restrict__ gkeys,
+             const int* __restrict__ gstart, int nq, int own_first, int n_own, GraphGrid g, float dist2,
+             int max_conn, int2* __restrict__ edges, int2* __restrict__ edge_slots, int capacity,
+             int* __restrict__ edge_count) {
+    int q = blockIdx.x * blockDim.x + threadIdx.x;
     int cand_id[CF_GRAPH_K];
-    int cand_slot[CF_GRAPH_K];
+    int cand_q[CF_GRAPH_K];
     float cand_d2[CF_GRAPH_K];
-    int ncand = 0;
-    int my_id = 0;
+    int ncand = 0, my_id = 0, my_slot = 0;
     const int K = 2 * max_conn;
-    if (active) {
-        float4 p = pos4[s];
-        my_id = id[s];
-        uint32_t ti = __float_as_uint(p.w);
-        int cx = cf_cell_coord_x(p.x, c);
-        int cy = cf_cell_coord(p.y, c.inv[1], c.dims[1]);
-        int cz = cf_cell_coord(p.z, c.inv[2], c.dims[2]);
-        int x0 = max(cx - m, c.gx_lo), x1 = min(cx + m, c.gx_hi);
-        int y0 = max(cy - m, 0), y1 = min(cy + m, c.dims[1] - 1);
-        int z0 = max(cz - m, 0), z1 = min(cz + m, c.dims[2] - 1);
-        for (int x = x0; x <= x1; x++)
-            for (int y = y0; y <= y1; y++) {
-                int row = (x * c.dims[1] + y) * c.dims[2];
-                // z-adjacent cells are contiguous in the sorted array: one range per (x, y)
-                int j0 = cell_start[row + z0], j1 = cell_start[row + z1 + 1];
-                for (int j = j0; j < j1; j++) {
-                    float4 o = pos4[j];
-                    if (__float_as_uint(o.w) != ti) continue;
-                    int jid = id[j];
-                    if (jid <= my_id) continue;
-                    float dx = __fsub_rn(o.x, p.x), dy = __fsub_rn(o.y, p.y), dz = __fsub_rn(o.z, p.z);
-                    float d2 = cf_dist2(dx, dy, dz);
-                    if (!(d2 < dist2)) continue;
-                    if (ncand == K && jid > cand_id[K - 1]) continue;
-                    // insert into the id-sorted candidate list (drop the largest id when full)
-                    int pos = ncand < K ? ncand : K - 1;
-                    while (pos > 0 && cand_id[pos - 1] > jid) {
-                        cand_id[pos] = cand_id[pos - 1];
-                        cand_slot[pos] = cand_slot[pos - 1];
-                        cand_d2[pos] = cand_d2[pos - 1];
-                        pos--;
+    bool active = false;
+    if (q < nq) {
+        uint32_t key = gkeys[q];
+        my_slot = (int)gvals[q];
+        active = key < (uint32_t)g.T * (uint32_t)g.ncell && my_slot >= own_first && my_slot < own_first + n_own;
+        if (active) {
+            float4 p = gpos[q];
+            my_id = __float_as_int(p.w);
+            int t = (int)(key / (uint32_t)g.ncell);
+            int cell = (int)(key - (uint32_t)t * (uint32_t)g.ncell);
+            int cz = cell % g.dims[2], cy = (cell / g.dims[2]) % g.dims[1], cx = cell / (g.dims[2] * g.dims[1]);
+            int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.dims[0] - 1);
+            int y0 = max(cy - 1, 0), y1 = min(cy + 1, g.dims[1] - 1);
+            int z0 = max(cz - 1, 0), z1 = min(cz + 1, g.dims[2] - 1);
+            const int tbase = t * g.ncell;
+            for (int x = x0; x <= x1; x++)
+                for (int y = y0; y <= y1; y++) {
+                    int row = tbase + (x * g.dims[1] + y) * g.dims[2];
+                    // z-adjacent cells of one type are contiguous: one range per (x, y)
+                    int j0 = gstart[row + z0], j1 = gstart[row + z1 + 1];
+                    for (int j = j0; j < j1; j++) {
+                        float4 o = gpos[j];
+                        int jid = __float_as_int(o.w);
+                        if (jid <= my_id) continue;
+                        float dx = __fsub_rn(o.x, p.x), dy = __fsub_rn(o.y, p.y), dz = __fsub_rn(o.z, p.z);
+                        float d2 = cf_dist2(dx, dy, dz);
+                        if (!(d2 < dist2)) continue;
+                        if (ncand == K && jid > cand_id[K - 1]) continue;
+                        // insert into the id-sorted candidate list (drop the largest id when full)
+                        int pos = ncand < K ? ncand : K - 1;
+                        while (pos > 0 && cand_id[pos - 1] > jid) {
+                            cand_id[pos] = cand_id[pos - 1];
+                            cand_q[pos] = cand_q[pos - 1];
+                            cand_d2[pos] = cand_d2[pos - 1];
+                            pos--;
+                        }
+                        cand_id[pos] = jid;
+                        cand_q[pos] = j;
+                        cand_d2[pos] = d2;
+                        if (ncand < K) ncand++;
                     }
-                    cand_id[pos] = jid;
-                    cand_slot[pos] = j;
-                    cand_d2[pos] = d2;
-                    if (ncand < K) ncand++;
                 }
+            // stable insertion sort by d2 (.cu:235-243); the list is in index order, as the
+            // reference's scan would have produced it
+            for (int a = 1; a < ncand; a++) {
+                float kd = cand_d2[a];
+                int ki = cand_id[a], kq = cand_q[a];
+                int b = a - 1;
+                while (b >= 0 && cand_d2[b] > kd) {
+                    cand_d2[b + 1] = cand_d2[b];
+                    cand_id[b + 1] = cand_id[b];
+                    cand_q[b + 1] = cand_q[b];
+                    b--;
+                }
+                cand_d2[b + 1] = kd;
+                cand_id[b + 1] = ki;
+                cand_q[b + 1] = kq;
             }
-        // stable insertion sort by d2 (.cu:235-243); the list is in index order, as the
-        // reference's scan would have produced it
-        for (int a = 1; a < ncand; a++) {
-            float kd = cand_d2[a];
-            int ki = cand_id[a], ks = cand_slot[a];
-            int b = a - 1;
-            while (b >= 0 && cand_d2[b] > kd) {
-                cand_d2[b + 1] = cand_d2[b];
-                cand_id[b + 1] = cand_id[b];
-                cand_slot[b + 1] = cand_slot[b];
-                b--;
-            }
-            cand_d2[b + 1] = kd;
-            cand_id[b + 1] = ki;
-            cand_slot[b + 1] = ks;
         }
     }
     int w = active ? min(ncand, max_conn) : 0;
@@ -97,7 +161,7 @@ graph_kernel(const float4* __restrict__ pos4, const int* __restrict__ id, const 
         int e = off + a;
         if (e < capacity) {
             edges[e] = make_int2(my_id, cand_id[a]);
-            edge_slots[e] = make_int2(s, cand_slot[a]);
+            edge_slots[e] = make_int2(my_slot, (int)gvals[cand_q[a]]);
         }
     }
 }
