@@ -177,7 +177,9 @@ def run_ours(args):
     sim.initializeParticles(seed=seed, mode=mode)
     if args.force_kernel:
         sim.setOption("force_kernel", args.force_kernel)
-    sim.setOption("timing", 1)
+    if args.no_graphs:
+        sim.setOption("cuda_graphs", 0)
+    sim.setOption("timing", 2)   # whole-step events; the step itself replays a CUDA graph
 
     def one_step():
         sim.simulate(sync=False)
@@ -205,10 +207,19 @@ def run_ours(args):
     step_ms = st.ms_total / max(st.steps, 1) + graph_ms / args.steps
     value = n / (step_ms * 1e-3)
     launches = int(st.launches)
+    # per-phase breakdown: a few extra steps launched kernel by kernel with events between phases
+    sim.setOption("timing", 1)
+    sim.statsReset()
+    for _ in range(5):
+        _lib.check(L.cf_bench_flush_l2(C.c_int(dev), C.c_size_t(L2_FLUSH)))
+        one_step()
+        sim.sync()
+    st = sim.stats()
     force_ms = st.ms_force / max(st.steps, 1)
     sort_ms = st.ms_sort / max(st.steps, 1)
     integ_ms = st.ms_integrate / max(st.steps, 1)
     accepted, tested = int(st.accepted_pairs), int(st.tested_pairs)
+    sim.setOption("timing", 2)
 
     # ---- roofline of the dominant kernel (pair force): 37 flop per accepted ordered pair -----
     tf = C.c_double(0)
@@ -407,6 +418,7 @@ def main():
     ap.add_argument("--force-kernel", type=int, default=0, help="0 auto, 1 per-particle, 2 tile")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-graphs", action="store_true", help="launch every kernel individually")
     ap.add_argument("--ref-cpu", action="store_true", help="reference arm on the CPU oracle port instead")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

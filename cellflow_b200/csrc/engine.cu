@@ -138,11 +138,22 @@ struct cf_sim {
     long long n_total = 0;         // global particle count (slab mode)
     double ms_exchange = 0;
 
+    // CUDA graphs of the (static) single-GPU step sequence: small problems are launch-bound
+    struct StepGraph {
+        cudaGraphExec_t exec = nullptr;
+        std::vector<char> sig;      // everything the captured launches depend on
+        std::vector<char> seen;     // signature met once (buffers sized): capture next time
+        long long nodes = 0;
+        bool swap_keys = false;
+    };
+    StepGraph step_graphs[4];
+    int opt_graphs = 1;
+
     // options
     int opt_stencil = 0;     // reserved (0 = automatic)
     int opt_force_kernel = 0; // 0 auto, 1 per-particle, 2 tile
     int opt_timing = 0;
-    double opt_max_cells_per_particle = 0.5;
+    double opt_max_cells_per_particle = 16.0; // fine grids pay off for clustered states (cells are cheap)
 
     // stats
     std::vector<StepEvents> ev_pool;
@@ -439,6 +450,15 @@ static int prepare_step_const(cf_sim* s) {
 // ---------------------------------------------------------------------------------------------
 // cell-list build
 // ---------------------------------------------------------------------------------------------
+// Items per sort block: 4096 for large inputs (<= 1024 blocks, small histograms); small inputs get
+// smaller blocks so that about one block per SM exists.
+static int sort_items_per_block(int n) {
+    int items = 4096;
+    while (items > 256 && div_up(n, items) < 148) items /= 2; // the single-block scan grows with nblocks
+    while (div_up(n, items) > 1024) items *= 2;
+    return items;
+}
+
 static int ensure_sorted(cf_sim* s) {
     if (s->sorted_valid) return 0;
     int n = s->n;
@@ -450,8 +470,7 @@ static int ensure_sorted(cf_sim* s) {
     while ((1ll << bits) < (long long)s->ncell * CF_KEY_SUB) bits++;
     int passes = div_up(bits, 8);
     int bits_per_pass = div_up(bits, passes);
-    int items = 4096;
-    while (div_up(n, items) > 1024) items *= 2;
+    int items = sort_items_per_block(n);
     int nblocks = div_up(n, items);
     size_t hist_need = (size_t)RS_BINS * nblocks;
     if (hist_need > s->hist_cap) {
@@ -569,6 +588,8 @@ extern "C" int cf_destroy(cf_sim* s) {
     if (!s) return CF_OK;
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
+    for (auto& g : s->step_graphs)
+        if (g.exec) cudaGraphExecDestroy(g.exec);
     slab_free(s);
     free_particle_buffers(s);
     cudaFree(s->hist);
@@ -887,6 +908,107 @@ static int launch_force(cf_sim* s) {
     return 0;
 }
 
+// One step, launched kernel by kernel.  Host-side state it changes: cur, keys/vals order,
+// sorted_valid (mirrored by replay_step_host_state for graph replays).
+static int step_direct(cf_sim* s, StepEvents* ev) {
+    if (ev) CU(cudaEventRecord(ev->e[0], s->stream));
+    if (ev) ev->has_exchange = s->slab && !s->sorted_valid;
+    if (int rc = build_cell_list(s, ev ? ev->e[4] : nullptr, ev ? ev->e[5] : nullptr)) return rc;
+    if (ev) CU(cudaEventRecord(ev->e[1], s->stream));
+    if (s->n > 0)
+        if (int rc = launch_force(s)) return rc;
+    if (ev) CU(cudaEventRecord(ev->e[2], s->stream));
+    if (s->n > 0) LAUNCH(s, integrate_kernel, div_up(s->n, 256), 256, 0, opos(s), ovel(s), ofrc(s), s->n, s->sc);
+    if (ev) CU(cudaEventRecord(ev->e[3], s->stream));
+    s->sorted_valid = false;
+    return 0;
+}
+
+static std::vector<char> step_signature(const cf_sim* s) {
+    std::vector<char> sig;
+    auto put = [&](const void* p, size_t n) { sig.insert(sig.end(), (const char*)p, (const char*)p + n); };
+    put(&s->sc, sizeof(s->sc));
+    const void* ptrs[] = {s->pos[0], s->pos[1], s->vel[0], s->vel[1], s->id[0], s->id[1], s->frc, s->keys[0],
+                          s->keys[1], s->vals[0], s->vals[1], s->hist, s->cell_start, s->d_tiles, s->d_tile_ctrl,
+                          s->d_tables, s->d_half};
+    put(ptrs, sizeof(ptrs));
+    int ints[] = {s->n, s->ncell, s->cur, s->opt_force_kernel, s->sorted_valid ? 1 : 0, s->half_bound_ok ? 1 : 0};
+    put(ints, sizeof(ints));
+    return sig;
+}
+
+// Steps of the single-GPU engine are a fixed kernel sequence for fixed parameters, so after one
+// direct run (which sizes every buffer) the sequence is captured into a CUDA graph and replayed:
+// ~15 launches become one, which is what bounds ms/step at 100 k particles and below.
+static int step_graphed(cf_sim* s, StepEvents* ev) {
+    std::vector<char> sig = step_signature(s);
+    cf_sim::StepGraph* hit = nullptr;
+    cf_sim::StepGraph* seen = nullptr;
+    cf_sim::StepGraph* spare = nullptr;
+    for (auto& g : s->step_graphs) {
+        if (g.exec && g.sig == sig) hit = &g;
+        else if (!g.exec && g.seen == sig) seen = &g;
+        else if (!g.exec && g.seen.empty() && !spare) spare = &g;
+    }
+    if (hit) {
+        if (ev) {
+            CU(cudaEventRecord(ev->e[0], s->stream));
+            CU(cudaEventRecord(ev->e[1], s->stream));
+            CU(cudaEventRecord(ev->e[2], s->stream));
+            ev->has_exchange = false;
+        }
+        CU(cudaGraphLaunch(hit->exec, s->stream));
+        if (ev) CU(cudaEventRecord(ev->e[3], s->stream));
+        if (!s->sorted_valid) { // what ensure_sorted does on the host
+            if (hit->swap_keys) std::swap(s->keys[0], s->keys[1]), std::swap(s->vals[0], s->vals[1]);
+            s->cur ^= 1;
+        }
+        s->sorted_valid = false;
+        s->launches += hit->nodes;
+        return 0;
+    }
+    if (seen) {
+        uint32_t* k0 = s->keys[0];
+        long long before = s->launches;
+        if (ev) {
+            CU(cudaEventRecord(ev->e[0], s->stream));
+            CU(cudaEventRecord(ev->e[1], s->stream));
+            CU(cudaEventRecord(ev->e[2], s->stream));
+            ev->has_exchange = false;
+        }
+        CU(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
+        int rc = step_direct(s, nullptr);
+        cudaGraph_t graph = nullptr;
+        cudaError_t e = cudaStreamEndCapture(s->stream, &graph);
+        if (rc) {
+            if (graph) cudaGraphDestroy(graph);
+            return rc;
+        }
+        if (e != cudaSuccess) return fail(CF_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
+        e = cudaGraphInstantiate(&seen->exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) return fail(CF_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e));
+        seen->sig = sig;
+        seen->seen.clear();
+        seen->nodes = s->launches - before;
+        seen->swap_keys = s->keys[0] != k0;
+        CU(cudaGraphLaunch(seen->exec, s->stream)); // the capture recorded, it did not run
+        if (ev) CU(cudaEventRecord(ev->e[3], s->stream));
+        return 0;
+    }
+    // first time with these parameters: run directly (allocations happen here), remember it
+    if (!spare) { // all slots taken by other signatures: recycle them
+        for (auto& g : s->step_graphs) {
+            if (g.exec) cudaGraphExecDestroy(g.exec);
+            g = cf_sim::StepGraph();
+        }
+        spare = &s->step_graphs[0];
+    }
+    int rc = step_direct(s, ev);
+    spare->seen = sig;
+    return rc;
+}
+
 extern "C" int cf_step(cf_sim* s, const cf_params* p, int n_steps) {
     ARG(s && n_steps >= 0);
     if (p) {
@@ -895,18 +1017,11 @@ extern "C" int cf_step(cf_sim* s, const cf_params* p, int n_steps) {
     if (int rc = set_device(s)) return rc;
     if (int rc = prepare_step_const(s)) return rc;
     if (s->n == 0 && !s->slab) return CF_OK;
+    // per-phase timing (timing == 1) needs the individual launches; timing == 2 times whole steps
+    const bool graphs = s->opt_graphs && !s->slab && s->opt_timing != 1 && s->n > 0;
     for (int it = 0; it < n_steps; it++) {
         StepEvents* ev = next_events(s);
-        if (ev) CU(cudaEventRecord(ev->e[0], s->stream));
-        if (ev) ev->has_exchange = s->slab && !s->sorted_valid;
-        if (int rc = build_cell_list(s, ev ? ev->e[4] : nullptr, ev ? ev->e[5] : nullptr)) return rc;
-        if (ev) CU(cudaEventRecord(ev->e[1], s->stream));
-        if (s->n > 0)
-            if (int rc = launch_force(s)) return rc;
-        if (ev) CU(cudaEventRecord(ev->e[2], s->stream));
-        if (s->n > 0) LAUNCH(s, integrate_kernel, div_up(s->n, 256), 256, 0, opos(s), ovel(s), ofrc(s), s->n, s->sc);
-        if (ev) CU(cudaEventRecord(ev->e[3], s->stream));
-        s->sorted_valid = false;
+        if (int rc = graphs ? step_graphed(s, ev) : step_direct(s, ev)) return rc;
     }
     CU(cudaGetLastError());
     return CF_OK;
@@ -1027,7 +1142,7 @@ extern "C" int cf_build_graph(cf_sim* s, float dist, int max_conn, int* n_edges)
         if (int rc = radix_sort_pairs(s, s->gk, s->gv, count, (long long)nkeys + 1, &src)) return rc;
         LAUNCH(s, graph_gather_kernel, div_up(count, 256), 256, 0, s->gv[src], s->pos[s->cur], s->id[s->cur], count, s->gpos);
         LAUNCH(s, graph_bounds_kernel, div_up(nkeys + 1, 256), 256, 0, s->gk[src], count, s->gstart, nkeys);
-        LAUNCH(s, graph_kernel, div_up(count, 128), 128, 0, s->gpos, s->gv[src], s->gk[src], s->gstart, count, s->base,
+        LAUNCH(s, graph_kernel, div_up(count, CF_GRAPH_THREADS), CF_GRAPH_THREADS, 0, s->gpos, s->gv[src], s->gk[src], s->gstart, count, s->base,
                s->n, g, dist * dist, mc, s->edges, s->edge_slots, s->edge_cap, s->d_edge_count);
     }
     if (s->opt_timing) {
@@ -1104,6 +1219,7 @@ extern "C" int cf_set_option(cf_sim* s, const char* name, double value) {
     else if (k == "force_kernel") s->opt_force_kernel = (int)value;
     else if (k == "timing") s->opt_timing = (int)value;
     else if (k == "max_cells_per_particle") s->opt_max_cells_per_particle = value;
+    else if (k == "cuda_graphs") s->opt_graphs = (int)value;
     else if (k == "halo_capacity") s->cap_halo = (int)value;       // before cf_comm_init
     else if (k == "migrant_capacity") s->cap_mig = (int)value;     // before cf_comm_init
     else return fail(CF_ERR_ARG, "unknown option '%s'", name);

@@ -73,15 +73,29 @@ __global__ void graph_bounds_kernel(const uint32_t* __restrict__ skeys, int n, i
 
 // One thread per graph-order position q (threads of a warp share a cell: candidate loads are
 // warp-uniform broadcasts).  Only owned particles (slot in [own_first, own_first + n_own)) emit.
-__global__ void __launch_bounds__(128)
+// The per-thread candidate lists live in shared memory, laid out [entry][thread]: dynamic
+// indexing costs one conflict-free LDS/STS instead of a scattered local-memory transaction
+// per lane (the first version kept them in local memory and spent most of its time there).
+#define CF_GRAPH_THREADS 64
+struct GraphList {
+    int* id;
+    int* q;
+    float* d2;
+    __device__ __forceinline__ int& I(int k) { return id[k * CF_GRAPH_THREADS]; }
+    __device__ __forceinline__ int& Q(int k) { return q[k * CF_GRAPH_THREADS]; }
+    __device__ __forceinline__ float& D(int k) { return d2[k * CF_GRAPH_THREADS]; }
+};
+
+__global__ void __launch_bounds__(CF_GRAPH_THREADS)
 graph_kernel(const float4* __restrict__ gpos, const uint32_t* __restrict__ gvals, const uint32_t* __restrict__ gkeys,
              const int* __restrict__ gstart, int nq, int own_first, int n_own, GraphGrid g, float dist2,
              int max_conn, int2* __restrict__ edges, int2* __restrict__ edge_slots, int capacity,
              int* __restrict__ edge_count) {
+    __shared__ int s_id[CF_GRAPH_K * CF_GRAPH_THREADS];
+    __shared__ int s_q[CF_GRAPH_K * CF_GRAPH_THREADS];
+    __shared__ float s_d2[CF_GRAPH_K * CF_GRAPH_THREADS];
+    GraphList L{s_id + threadIdx.x, s_q + threadIdx.x, s_d2 + threadIdx.x};
     int q = blockIdx.x * blockDim.x + threadIdx.x;
-    int cand_id[CF_GRAPH_K];
-    int cand_q[CF_GRAPH_K];
-    float cand_d2[CF_GRAPH_K];
     int ncand = 0, my_id = 0, my_slot = 0;
     const int K = 2 * max_conn;
     bool active = false;
@@ -111,36 +125,36 @@ graph_kernel(const float4* __restrict__ gpos, const uint32_t* __restrict__ gvals
                         float dx = __fsub_rn(o.x, p.x), dy = __fsub_rn(o.y, p.y), dz = __fsub_rn(o.z, p.z);
                         float d2 = cf_dist2(dx, dy, dz);
                         if (!(d2 < dist2)) continue;
-                        if (ncand == K && jid > cand_id[K - 1]) continue;
+                        if (ncand == K && jid > L.I(K - 1)) continue;
                         // insert into the id-sorted candidate list (drop the largest id when full)
                         int pos = ncand < K ? ncand : K - 1;
-                        while (pos > 0 && cand_id[pos - 1] > jid) {
-                            cand_id[pos] = cand_id[pos - 1];
-                            cand_q[pos] = cand_q[pos - 1];
-                            cand_d2[pos] = cand_d2[pos - 1];
+                        while (pos > 0 && L.I(pos - 1) > jid) {
+                            L.I(pos) = L.I(pos - 1);
+                            L.Q(pos) = L.Q(pos - 1);
+                            L.D(pos) = L.D(pos - 1);
                             pos--;
                         }
-                        cand_id[pos] = jid;
-                        cand_q[pos] = j;
-                        cand_d2[pos] = d2;
+                        L.I(pos) = jid;
+                        L.Q(pos) = j;
+                        L.D(pos) = d2;
                         if (ncand < K) ncand++;
                     }
                 }
             // stable insertion sort by d2 (.cu:235-243); the list is in index order, as the
             // reference's scan would have produced it
             for (int a = 1; a < ncand; a++) {
-                float kd = cand_d2[a];
-                int ki = cand_id[a], kq = cand_q[a];
+                float kd = L.D(a);
+                int ki = L.I(a), kq = L.Q(a);
                 int b = a - 1;
-                while (b >= 0 && cand_d2[b] > kd) {
-                    cand_d2[b + 1] = cand_d2[b];
-                    cand_id[b + 1] = cand_id[b];
-                    cand_q[b + 1] = cand_q[b];
+                while (b >= 0 && L.D(b) > kd) {
+                    L.D(b + 1) = L.D(b);
+                    L.I(b + 1) = L.I(b);
+                    L.Q(b + 1) = L.Q(b);
                     b--;
                 }
-                cand_d2[b + 1] = kd;
-                cand_id[b + 1] = ki;
-                cand_q[b + 1] = kq;
+                L.D(b + 1) = kd;
+                L.I(b + 1) = ki;
+                L.Q(b + 1) = kq;
             }
         }
     }
@@ -160,8 +174,8 @@ graph_kernel(const float4* __restrict__ gpos, const uint32_t* __restrict__ gvals
     for (int a = 0; a < w; a++) {
         int e = off + a;
         if (e < capacity) {
-            edges[e] = make_int2(my_id, cand_id[a]);
-            edge_slots[e] = make_int2(my_slot, (int)gvals[cand_q[a]]);
+            edges[e] = make_int2(my_id, L.I(a));
+            edge_slots[e] = make_int2(my_slot, (int)gvals[L.Q(a)]);
         }
     }
 }

@@ -112,8 +112,7 @@ static int radix_sort_pairs(cf_sim* s, uint32_t* k[2], uint32_t* v[2], int n, lo
     while ((1ll << bits) < key_range) bits++;
     int passes = div_up(bits, 8);
     int bits_per_pass = div_up(bits, passes);
-    int items = 4096;
-    while (div_up(n, items) > 1024) items *= 2;
+    int items = sort_items_per_block(n);
     int nblocks = div_up(n, items);
     size_t hist_need = (size_t)RS_BINS * nblocks;
     if (hist_need > s->hist_cap) {
