@@ -155,17 +155,19 @@ __device__ __forceinline__ void tkw_force_pair(u64 dx, u64 dy, u64 dz, u64 d2, b
                                                const char* tab_i, int t0, int t1, float c2u, float bu,
                                                float repulsion, float attraction, float nk_log2e,
                                                u64& ax, u64& ay, u64& az, int& cnt) {
+    const u64 x2 = tk_add2(d2, tk_pack(0.0001f, 0.0001f));
     float x0, x1;
-    tk_unpack(tk_add2(d2, tk_pack(0.0001f, 0.0001f)), x0, x1);
-    float s0, s1;
+    tk_unpack(x2, x0, x1);
+    u64 s;
     if (UNIFORM) {
-        // s = fv * (rep * e / dist - att / Reff), e = exp2(c2 * x)
+        // s = fv * (rep * e / dist - att / Reff), e = exp2(c2 * x); packed except the two MUFUs
         float fv0 = *reinterpret_cast<const float*>(tab_i + t0);
         float fv1 = *reinterpret_cast<const float*>(tab_i + t1);
-        float r0 = cf_rsqrt(x0), r1 = cf_rsqrt(x1);
-        float e0 = cf_ex2(x0 * c2u), e1 = cf_ex2(x1 * c2u);
-        s0 = fv0 * fmaf(e0 * r0, repulsion, -bu);
-        s1 = fv1 * fmaf(e1 * r1, repulsion, -bu);
+        float t0f, t1f;
+        tk_unpack(tk_mul2(x2, tk_pack(c2u, c2u)), t0f, t1f);
+        const u64 er = tk_mul2(tk_pack(cf_ex2(t0f), cf_ex2(t1f)), tk_pack(cf_rsqrt(x0), cf_rsqrt(x1)));
+        const u64 u = tk_fma2(er, tk_pack(repulsion, repulsion), tk_pack(-bu, -bu));
+        s = tk_mul2(u, tk_pack(ok0 ? fv0 : 0.f, ok1 ? fv1 : 0.f)); // rejected pairs: exact 0
     } else {
         // table entry = (fv, 1/Reff, cut2, -): the exact accept test happens here
         float4 p0 = *reinterpret_cast<const float4*>(tab_i + t0);
@@ -174,15 +176,14 @@ __device__ __forceinline__ void tkw_force_pair(u64 dx, u64 dy, u64 dz, u64 d2, b
         tk_unpack(d2, a0, a1);
         ok0 = a0 < p0.z;
         ok1 = a1 < p1.z;
-        float r0 = cf_rsqrt(x0), r1 = cf_rsqrt(x1);
-        float e0 = cf_ex2(x0 * (nk_log2e * p0.y * p0.y)), e1 = cf_ex2(x1 * (nk_log2e * p1.y * p1.y));
-        s0 = p0.x * fmaf(e0 * r0, repulsion, -(attraction * p0.y));
-        s1 = p1.x * fmaf(e1 * r1, repulsion, -(attraction * p1.y));
+        const u64 inv = tk_pack(p0.y, p1.y);
+        float t0f, t1f;
+        tk_unpack(tk_mul2(x2, tk_mul2(tk_mul2(inv, inv), tk_pack(nk_log2e, nk_log2e))), t0f, t1f);
+        const u64 er = tk_mul2(tk_pack(cf_ex2(t0f), cf_ex2(t1f)), tk_pack(cf_rsqrt(x0), cf_rsqrt(x1)));
+        const u64 u = tk_fma2(er, tk_pack(repulsion, repulsion), tk_mul2(inv, tk_pack(-attraction, -attraction)));
+        s = tk_mul2(u, tk_pack(ok0 ? p0.x : 0.f, ok1 ? p1.x : 0.f));
     }
-    s0 = ok0 ? s0 : 0.f;
-    s1 = ok1 ? s1 : 0.f;
     cnt += (ok0 ? 1 : 0) + (ok1 ? 1 : 0);
-    u64 s = tk_pack(s0, s1);
     ax = tk_fma2(s, dx, ax);
     ay = tk_fma2(s, dy, ay);
     az = tk_fma2(s, dz, az);
