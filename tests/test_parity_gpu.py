@@ -275,3 +275,64 @@ def test_newton_third_law_with_symmetric_matrix():
     acc = sim.getParticleData()["acc"].astype(np.float64)
     assert np.abs(acc.sum(0)).max() <= 1e-5 * np.abs(acc).sum(0).max()
     sim.close()
+
+
+@pytest.mark.parametrize("tag", ["settings", "eater_radii_wrap", "defaults", "pulser_edge"])
+@pytest.mark.parametrize("kernel", [1, 2])
+def test_against_reference_kernel_golden(tag, kernel):
+    """The engine against the REFERENCE'S OWN kernel output (tests/golden, generated on a B200 by
+    the unmodified reference .cu one warp at a time): neighbour counts bit-exact, forces 1e-5."""
+    import ctypes as C
+    import os
+    z = np.load(os.path.join(U.GOLDEN, f"step_{tag}.npz"))
+    p = O.Params()
+    C.memmove(C.byref(p), z["params"].tobytes(), C.sizeof(p))
+    state, counts = z["state"].view(O.PARTICLE).reshape(-1), z["counts"]
+    ref, ref_cnt = z["out"].view(O.PARTICLE).reshape(-1), z["cnt"]
+    sim = make_sim(p, z["table"], z["radio"], state, counts, force_kernel=kernel)
+    sim.simulate()
+    got, gcnt = sim.getParticleData(), sim.getNeighborCounts()
+    assert np.array_equal(gcnt, ref_cnt)
+    _, _, fabs = O.step(state, counts, p, z["table"], z["radio"], "cells", THREADS)   # scale only
+    mult = U.force_multiplier_of(p, ref_cnt, counts)
+    assert U.force_rel_err(got["acc"], ref["acc"], fabs, mult).max() <= U.FORCE_RTOL
+    dp = U.wrapped_abs_diff(got["pos"], ref["pos"], p.canvas).max(axis=1)
+    quantum = float(np.spacing(np.float32(2 * p.canvas.max())))
+    assert np.all(dp <= p.delta_t * p.delta_t * U.FORCE_RTOL * np.abs(mult) * fabs + 1.01 * quantum)
+    sim.close()
+
+
+def test_graph_against_reference_kernel_golden():
+    import os
+    for tag in ("cube", "blobs"):
+        z = np.load(os.path.join(U.GOLDEN, f"graph_{tag}.npz"))
+        state = z["state"].view(O.PARTICLE).reshape(-1)
+        colors = z["colors"].view(cf.COLOR).reshape(-1)
+        p, table, radio = U.config("eater")
+        sim = make_sim(p, table, radio, state, np.zeros(len(state), np.int32))
+        edges, verts = sim.generateProximityGraph(float(z["dist"]), int(z["max_conn"]), colors)
+        rec = verts[np.lexsort(verts.T[::-1])]
+        assert np.array_equal(rec, z["records"])      # the reference's VBO content, as a set
+        sim.close()
+
+
+def test_empty_and_degenerate_inputs():
+    p, table, radio = U.config("eater")
+    sim = cf.ParticleSimulation(0, 6, init=False)       # no particles at all
+    sim.params = U.to_lib_params(p)
+    sim.simulate(steps=3)
+    assert len(sim.getParticleData()) == 0
+    edges, _ = sim.generateProximityGraph(200.0, 5)
+    assert len(edges) == 0
+    sim.close()
+    # one type only, everything in one cell, zero velocity
+    p1, t1, r1 = U.config("eater", numParticleTypes=1)
+    state, counts = U.random_state(500, 1, 3, p1.canvas, "cube", cube=100.0, vel_scale=0.0)
+    check_step(p1, np.float32([0.3]), np.float32([0.0]), state, counts)
+    # maxConn 0 and distance 0: no edges, no error
+    sim = make_sim(p, table, radio, *U.random_state(1000, 6, 1, p.canvas, "cube"))
+    assert len(sim.generateProximityGraph(200.0, 0)[0]) == 0
+    assert len(sim.generateProximityGraph(0.0, 5)[0]) == 0
+    with pytest.raises(cf.CellFlowError):
+        sim.setParticleData(np.zeros(10, cf.PARTICLE)[:0], None) if False else sim.setOption("nope", 1)
+    sim.close()
