@@ -13,6 +13,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <string>
 #include <vector>
 
@@ -136,6 +137,7 @@ struct cf_sim {
     int* h_slab_counts = nullptr;  // pinned mirror
     int n_ghost[2] = {0, 0};
     long long n_total = 0;         // global particle count (slab mode)
+    double halo_slack = 2.0, mig_slack = 1.0;
     double ms_exchange = 0;
 
     // CUDA graphs of the (static) single-GPU step sequence: small problems are launch-bound
@@ -590,6 +592,13 @@ extern "C" int cf_destroy(cf_sim* s) {
     if (s->stream) cudaStreamSynchronize(s->stream);
     for (auto& g : s->step_graphs)
         if (g.exec) cudaGraphExecDestroy(g.exec);
+    if (s->slab && getenv("CF_SLAB_DEBUG") && g_slab_times.calls > 5) {
+        double c = (double)(g_slab_times.calls - 5);
+        fprintf(stderr, "[cellflow_b200 rank %d] slab build x%lld: host total %.3f ms (wait own sort %.3f, wait migrants %.3f); "
+                        "device: migrant exchange %.3f ms, merge+reorder+bounds %.3f ms, halo exchange %.3f ms\n",
+                s->rank, g_slab_times.calls, 1e3 * g_slab_times.enqueue / c, 1e3 * g_slab_times.sort_sync / c,
+                1e3 * g_slab_times.mig_sync / c, g_slab_times.gpu_mig / c, g_slab_times.gpu_mid / c, g_slab_times.gpu_halo / c);
+    }
     slab_free(s);
     free_particle_buffers(s);
     cudaFree(s->hist);
@@ -1220,6 +1229,9 @@ extern "C" int cf_set_option(cf_sim* s, const char* name, double value) {
     else if (k == "timing") s->opt_timing = (int)value;
     else if (k == "max_cells_per_particle") s->opt_max_cells_per_particle = value;
     else if (k == "cuda_graphs") s->opt_graphs = (int)value;
+    else if (k == "global_particle_count") s->n_total = (long long)value; // same value on every rank
+    else if (k == "halo_slack") s->halo_slack = value;
+    else if (k == "migrant_slack") s->mig_slack = value;
     else if (k == "halo_capacity") s->cap_halo = (int)value;       // before cf_comm_init
     else if (k == "migrant_capacity") s->cap_mig = (int)value;     // before cf_comm_init
     else return fail(CF_ERR_ARG, "unknown option '%s'", name);

@@ -105,6 +105,24 @@ static int slab_exchange(cf_sim* s, char* send_left, char* send_right, char* rec
     return 0;
 }
 
+// Elements actually shipped per message.  Buffers are allocated for cap_halo / cap_mig, but a
+// fixed-size message of that capacity would move ~30 MB per step and rank; both ends of a link
+// instead derive the same tighter bound from numbers every rank knows (global count, world size,
+// owned layers): 2x the mean ghost layer + 8192, mean/64 + 16384 migrants.  A rank that would
+// exceed it fails with CF_ERR_CAPACITY (raise it with the halo_slack / migrant_slack options).
+static int slab_halo_msg_cap(const cf_sim* s) {
+    if (s->n_total <= 0) return s->cap_halo; // global count unknown: full (identical) capacity
+    double mean = (double)s->n_total / s->world / std::max(s->nxl, 1);
+    long long cap = (long long)(s->halo_slack * mean) + 8192;
+    return (int)std::min<long long>(cap, s->cap_halo);
+}
+static int slab_mig_msg_cap(const cf_sim* s) {
+    if (s->n_total <= 0) return s->cap_mig;
+    double mean = (double)s->n_total / s->world;
+    long long cap = (long long)(s->mig_slack * mean / 64.0) + 16384;
+    return (int)std::min<long long>(cap, s->cap_mig);
+}
+
 // Stable radix sort of (key, val) pairs held in keys[0]/vals[0] of the given buffers; returns the
 // index (0/1) of the buffer holding the result.
 static int radix_sort_pairs(cf_sim* s, uint32_t* k[2], uint32_t* v[2], int n, long long key_range, int* out_src) {
@@ -139,13 +157,31 @@ static int radix_sort_pairs(cf_sim* s, uint32_t* k[2], uint32_t* v[2], int n, lo
 static int slab_check_flags(cf_sim* s) {
     int f = s->h_slab_counts[3];
     if (f == 1) return fail(CF_ERR_STATE, "a particle moved further than one slab width in one step");
-    if (f == 2) return fail(CF_ERR_CAPACITY, "ghost layer larger than halo_capacity (%d)", s->cap_halo);
+    if (f == 2)
+        return fail(CF_ERR_CAPACITY, "a ghost layer exceeded the halo message capacity (%d): raise halo_slack",
+                    slab_halo_msg_cap(s));
     return 0;
+}
+
+// Host-side wall-clock breakdown of the slab cell-list build (CF_SLAB_DEBUG=1 prints it at
+// cf_destroy): where a rank waits — its own GPU (sync after the sort) or its neighbours.
+struct SlabHostTimes {
+    double sort_sync = 0, mig_sync = 0, enqueue = 0;
+    double gpu_mig = 0, gpu_mid = 0, gpu_halo = 0; // device time: migrant exchange, merge/reorder, halo exchange
+    long long calls = 0;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+};
+static thread_local SlabHostTimes g_slab_times;
+static double wall_now() {
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec + 1e-9 * ts.tv_nsec;
 }
 
 // Cell-list build in slab mode: classify + sort, migrate, merge, reorder, bounds, ghost exchange.
 static int ensure_sorted_slab(cf_sim* s, cudaEvent_t ev_x0, cudaEvent_t ev_x1) {
     if (s->sorted_valid) return 0;
+    const double t_begin = wall_now();
     const int cur = s->cur, nxt = cur ^ 1;
     const int B = s->base;
     int n = s->n;
@@ -162,25 +198,36 @@ static int ensure_sorted_slab(cf_sim* s, cudaEvent_t ev_x0, cudaEvent_t ev_x1) {
         CU(cudaMemsetAsync(s->d_slab_counts, 0, 3 * sizeof(int), s->stream));
     }
     CU(cudaMemcpyAsync(s->h_slab_counts, s->d_slab_counts, 4 * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    const double t_s0 = wall_now();
     CU(cudaStreamSynchronize(s->stream));
+    if (g_slab_times.calls >= 5) g_slab_times.sort_sync += wall_now() - t_s0;
     if (int rc = slab_check_flags(s)) return rc;
     n_stay = s->h_slab_counts[0], n_left = s->h_slab_counts[1], n_right = s->h_slab_counts[2];
-    if (n_left > s->cap_mig || n_right > s->cap_mig)
-        return fail(CF_ERR_CAPACITY, "%d/%d migrants exceed migrant_capacity (%d)", n_left, n_right, s->cap_mig);
+    const int mcap = slab_mig_msg_cap(s), hcap = slab_halo_msg_cap(s);
+    if (n_left > mcap || n_right > mcap)
+        return fail(CF_ERR_CAPACITY, "%d/%d migrants exceed the migrant message capacity (%d): raise migrant_slack",
+                    n_left, n_right, mcap);
 
     if (ev_x0) CU(cudaEventRecord(ev_x0, s->stream));
+    const bool dbg = getenv("CF_SLAB_DEBUG") != nullptr;
+    if (dbg && !g_slab_times.ev[0])
+        for (int i = 0; i < 4; i++) cudaEventCreate(&g_slab_times.ev[i]);
+    if (dbg) cudaEventRecord(g_slab_times.ev[0], s->stream);
     // ---- migrants ----
     LAUNCH(s, slab_pack_migrants_kernel, div_up(std::max(n_left + n_right, 1), 256), 256, 0, s->vals[src],
            s->pos[cur] + B, s->vel[cur] + B, s->id[cur] + B, n_stay, n_left, n_right, s->send_mig[0], s->send_mig[1],
-           s->cap_mig);
+           mcap);
     if (int rc = slab_exchange(s, s->send_mig[0], s->send_mig[1], s->recv_mig[0], s->recv_mig[1],
-                               slab_mig_bytes(s->cap_mig)))
+                               slab_mig_bytes(mcap)))
         return rc;
-    CU(cudaMemcpyAsync(&s->h_slab_counts[6], mig_count(s->recv_mig[0], s->cap_mig), sizeof(int),
+    CU(cudaMemcpyAsync(&s->h_slab_counts[6], mig_count(s->recv_mig[0], mcap), sizeof(int),
                        cudaMemcpyDeviceToHost, s->stream));
-    CU(cudaMemcpyAsync(&s->h_slab_counts[7], mig_count(s->recv_mig[1], s->cap_mig), sizeof(int),
+    CU(cudaMemcpyAsync(&s->h_slab_counts[7], mig_count(s->recv_mig[1], mcap), sizeof(int),
                        cudaMemcpyDeviceToHost, s->stream));
+    if (dbg) cudaEventRecord(g_slab_times.ev[1], s->stream);
+    const double t_s1 = wall_now();
     CU(cudaStreamSynchronize(s->stream));
+    if (g_slab_times.calls >= 5) g_slab_times.mig_sync += wall_now() - t_s1;
     const int n_al = s->h_slab_counts[6], n_ar = s->h_slab_counts[7], n_a = n_al + n_ar;
     const int n_new = n_stay + n_a;
     if (n + n_a > s->cap_own || n_new > s->cap_own)
@@ -190,7 +237,7 @@ static int ensure_sorted_slab(cf_sim* s, cudaEvent_t ev_x0, cudaEvent_t ev_x1) {
     uint32_t* fvals = s->vals[src];
     if (n_a > 0) {
         LAUNCH(s, slab_unpack_arrivals_kernel, div_up(n_a, 256), 256, 0, s->recv_mig[0], s->recv_mig[1], n_al, n_ar,
-               s->cap_mig, s->pos[cur] + B, s->vel[cur] + B, s->id[cur] + B, n, s->akeys[0], s->avals[0], s->sc);
+               mcap, s->pos[cur] + B, s->vel[cur] + B, s->id[cur] + B, n, s->akeys[0], s->avals[0], s->sc);
         int asrc = 0;
         if (int rc = radix_sort_pairs(s, s->akeys, s->avals, n_a, KC, &asrc)) return rc;
         LAUNCH(s, slab_merge_kernel, div_up(n_new, 256), 256, 0, s->keys[src], s->vals[src], n_stay, s->akeys[asrc],
@@ -209,19 +256,31 @@ static int ensure_sorted_slab(cf_sim* s, cudaEvent_t ev_x0, cudaEvent_t ev_x1) {
     s->n = n_new;
 
     // ---- ghost layers ----
+    if (dbg) cudaEventRecord(g_slab_times.ev[2], s->stream);
     const int layer_cells = s->sc.dims[1] * s->sc.dims[2];
-    LAUNCH(s, slab_pack_halo_kernel, div_up(s->cap_halo, 256), 256, 0, s->pos[nxt], s->id[nxt], s->cell_start,
-           layer_cells, s->nxl, s->send_halo[0], s->send_halo[1], s->cap_halo, s->d_slab_counts + 3);
+    LAUNCH(s, slab_pack_halo_kernel, div_up(hcap, 256), 256, 0, s->pos[nxt], s->id[nxt], s->cell_start,
+           layer_cells, s->nxl, s->send_halo[0], s->send_halo[1], hcap, s->d_slab_counts + 3);
     if (int rc = slab_exchange(s, s->send_halo[0], s->send_halo[1], s->recv_halo[0], s->recv_halo[1],
-                               slab_halo_bytes(s->cap_halo)))
+                               slab_halo_bytes(hcap)))
         return rc;
-    LAUNCH(s, slab_unpack_ghosts_kernel, div_up(s->cap_halo, 256), 256, 0, s->recv_halo[0], s->recv_halo[1], s->cap_halo,
+    LAUNCH(s, slab_unpack_ghosts_kernel, div_up(hcap, 256), 256, 0, s->recv_halo[0], s->recv_halo[1], hcap,
            s->pos[nxt], s->id[nxt], B, n_new, s->gkeys[0], s->gkeys[1], s->sc);
     LAUNCH(s, slab_ghost_bounds_kernel, div_up(2 * layer_cells + 1, 256), 256, 0, s->gkeys[0], s->gkeys[1],
-           s->recv_halo[0], s->recv_halo[1], s->cap_halo, s->cell_start, layer_cells, s->ncell, B, n_new, s->d_slab_counts + 4);
+           s->recv_halo[0], s->recv_halo[1], hcap, s->cell_start, layer_cells, s->ncell, B, n_new, s->d_slab_counts + 4);
     if (ev_x1) CU(cudaEventRecord(ev_x1, s->stream));
     s->sorted_valid = true;
     CU(cudaGetLastError());
+    if (dbg) {
+        cudaEventRecord(g_slab_times.ev[3], s->stream);
+        cudaEventSynchronize(g_slab_times.ev[3]);
+        float a = 0, b = 0, c = 0;
+        cudaEventElapsedTime(&a, g_slab_times.ev[0], g_slab_times.ev[1]);
+        cudaEventElapsedTime(&b, g_slab_times.ev[1], g_slab_times.ev[2]);
+        cudaEventElapsedTime(&c, g_slab_times.ev[2], g_slab_times.ev[3]);
+        if (g_slab_times.calls >= 5) g_slab_times.gpu_mig += a, g_slab_times.gpu_mid += b, g_slab_times.gpu_halo += c;
+    }
+    if (g_slab_times.calls >= 5) g_slab_times.enqueue += wall_now() - t_begin;
+    g_slab_times.calls++;
     return 0;
 }
 

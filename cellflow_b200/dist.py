@@ -171,6 +171,7 @@ def make_slab_sim(params, raw, radio, n_total, seed, mode, capacity_factor=1.5, 
     ident = nccl_unique_id() if world > 1 else None
     capacity = int(n_total / world * capacity_factor) + 1024
     sim.commInit(rank, world, ident, capacity)
+    sim.setOption("global_particle_count", n_total)   # lets both ends of a link agree on tight message sizes
     if seed is not None:
         sim.initParticlesGlobal(n_total, seed, mode)
     return sim, rank, world

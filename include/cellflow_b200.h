@@ -223,7 +223,9 @@ int cf_apply_preset(cf_sim* sim, const cf_preset* preset);
 
 int cf_nccl_unique_id(void* id128);  /* 128 bytes; rank 0 creates, host broadcasts */
 /* Rank `rank` of `world` owns x in [rank*W/world, (rank+1)*W/world).  `capacity` bounds the
- * owned particle count of this rank. */
+ * owned particle count of this rank and must be the same on every rank (message sizes derive
+ * from it, or from the option "global_particle_count" when that is set, identically, on all
+ * ranks). */
 int cf_comm_init(cf_sim* sim, int rank, int world, const void* id128, int capacity);
 /* Slab-mode initial condition: every rank generates the same n_total particles (counter-based
  * generator) and keeps those whose x lies in its slab.  Canvas = params last set. */
