@@ -1,24 +1,26 @@
 // kernels_tile.cuh — tiled pair-force kernel for dense cells (the FP32-bound hot kernel).
 //
 // Work decomposition
-//   tile  = up to TK_TI (512) particles of ONE cell ("i" side), handled by one 128-thread CTA;
-//           every thread keeps TK_IPT = 4 i-particles and their force/count accumulators in
+//   tile  = up to TK_TI (128) particles of ONE cell ("i" side), owned by one WARP: every lane
+//           keeps TK_IPT = 4 i-particles (4 "layers" of 32) and their force/count accumulators in
 //           registers.  Tiles come from a device-built list, fetched with an atomic counter by a
 //           persistent grid (clustered states make cells wildly uneven: work-based scheduling).
 //   j side = the 27 neighbour cells as <= 18 contiguous runs of the sorted array (cells that are
-//           adjacent in z are adjacent in memory), streamed through double-buffered shared
-//           memory in chunks of 128 particles, SoA (xs, ys, zs, type[, half-radius]).
+//           adjacent in z are adjacent in memory), streamed through a warp-private double buffer
+//           in shared memory, 64 particles per chunk, SoA (xs, ys, zs, table row[, half-radius]).
 //
-// Why it looks like this (measured on B200, profiles/r01_pipe_microbench.txt)
+// Why it looks like this (measured on B200, profiles/r01_pipe_microbench.txt and
+// profiles/r01_force_kernel_history.md)
 //   * shared->register bandwidth is one 32-bit word per lane per clock per SM: an LDS.128
 //     broadcast costs ~4 SM-cycles.  With one i per lane the j stream alone would need 2x the
 //     cycles of the arithmetic, hence 4 i per lane (each loaded j is used 4x32 times).
 //   * FFMA2/FADD2/FMUL2 (fma.rn.f32x2 ...) run at the same lane rate as the scalar forms but
-//     take half the issue slots, which lets compares, mask updates and LDS issue for free
-//     beside a saturated FMA pipe.  j particles are processed in packed pairs (x0,x1).
-//   * ~85% of tested pairs are out of range.  The test phase only records accept bits
-//     (one 64-bit mask per i per 64 j); the force terms are evaluated afterwards for the set
-//     bits only, so the expensive path never runs predicated-off for rejected pairs.
+//     take half the issue slots, which lets compares and LDS issue for free beside a busy FMA
+//     pipe.  j particles are processed in packed pairs (x0,x1).
+//   * ~85-93% of tested pairs are out of range, and a per-lane "collect accept bits, then drain"
+//     scheme ran its drain loop at 7 of 32 lanes.  Instead the sort puts particles in Morton
+//     order inside each cell, so that a layer (32 i) and a quad (4 j) are compact blobs, and ONE
+//     warp vote per (layer, quad) decides whether the force terms are evaluated at all.
 //
 // Exactness: displacement = (jx + (-px)) [+ s], s in {-W, 0, +W} per run.  For a periodic axis
 // with >= 4 cells the reference's two-sided wrap test (.cu:97-98) is decided by which neighbour
@@ -59,18 +61,6 @@ __device__ __forceinline__ u64 tk_fma2(u64 a, u64 b, u64 c) {
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
     return d;
 }
-
-struct TileRun {
-    int j0, j1;       // slot range of the run
-    float sx, sy, sz; // exact minimum-image shift of the run
-    int wrap;         // any shift non-zero
-};
-
-// Per type pair: A = repulsion * fv, B = attraction * fv / Reff, c2 = -k log2(e) / Reff^2, cut2.
-// s = fv * net / dist = A * e / dist - B  with  e = exp2(c2 * (d2 + 1e-4)).
-struct TilePairConst {
-    float A, B, c2, cut2;
-};
 
 // Pair tests executed by a 27-cell stencil pass: sum over cells of n_cell * (particles in the
 // distinct neighbour cells).  Used for the tested-pairs figure of cf_get_stats.
