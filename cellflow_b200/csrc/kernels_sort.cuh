@@ -33,59 +33,88 @@ rs_hist_kernel(const uint32_t* __restrict__ keys, int n, int shift, uint32_t mas
 }
 
 // In-place exclusive scan of `total` counters by one block of 1024 threads, in coalesced tiles of
-// 4096 (one uint4 per thread): thread-local prefix, warp shuffle scan, 32 warp totals scanned by
-// warp 0, running carry between tiles.  (A chunk-per-thread version read with a stride of
-// total/1024 words and took 52 us for 62 k counters; this one is bandwidth-limited.)
+// 16384 (four uint4 per thread, each uint4 load/store warp-contiguous): thread-local prefix,
+// warp shuffle scan, 32 warp totals scanned by warp 0, running carry between tiles.  (A
+// chunk-per-thread version read with a stride of total/1024 words and took 52 us for 62 k
+// counters; a 4096-wide tiled one was bound by its three barriers per tile.)
+#define RS_SCAN_VEC 4
 __global__ void __launch_bounds__(1024) rs_scan_kernel(uint32_t* __restrict__ hist, int total) {
     __shared__ uint32_t warp_sums[32];
     __shared__ uint32_t carry_s;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) carry_s = 0;
     __syncthreads();
-    for (int base = 0; base < total; base += 4096) {
-        const int i = base + 4 * tid;
-        uint32_t v0 = 0, v1 = 0, v2 = 0, v3 = 0;
-        if (i + 3 < total && (total & 3) == 0) {
-            uint4 v = *reinterpret_cast<const uint4*>(hist + i);
-            v0 = v.x, v1 = v.y, v2 = v.z, v3 = v.w;
-        } else {
-            if (i < total) v0 = hist[i];
-            if (i + 1 < total) v1 = hist[i + 1];
-            if (i + 2 < total) v2 = hist[i + 2];
-            if (i + 3 < total) v3 = hist[i + 3];
-        }
-        const uint32_t sum = v0 + v1 + v2 + v3;
-        uint32_t incl = sum;
+    const bool vec_ok = (total & 3) == 0;
+    for (int base = 0; base < total; base += 4096 * RS_SCAN_VEC) {
+        // thread owns RS_SCAN_VEC groups of 4 consecutive counters: group g starts at
+        // base + g*4096 + 4*tid, so the scan order inside a tile is (g, tid, element)
+        uint32_t v[RS_SCAN_VEC][4];
+        uint32_t gsum[RS_SCAN_VEC];
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += t;
+        for (int g = 0; g < RS_SCAN_VEC; g++) {
+            const int i = base + g * 4096 + 4 * tid;
+            v[g][0] = v[g][1] = v[g][2] = v[g][3] = 0;
+            if (vec_ok && i + 3 < total) {
+                uint4 q = *reinterpret_cast<const uint4*>(hist + i);
+                v[g][0] = q.x, v[g][1] = q.y, v[g][2] = q.z, v[g][3] = q.w;
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; e++)
+                    if (i + e < total) v[g][e] = hist[i + e];
+            }
+            gsum[g] = v[g][0] + v[g][1] + v[g][2] + v[g][3];
         }
         const uint32_t carry = carry_s; // final since the barrier that ended the previous tile
-        if (lane == 31) warp_sums[warp] = incl;
+        // inclusive scan of every group across the block (4 independent scans share the barriers)
+        uint32_t incl[RS_SCAN_VEC];
+#pragma unroll
+        for (int g = 0; g < RS_SCAN_VEC; g++) {
+            uint32_t x = gsum[g];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t t = __shfl_up_sync(0xffffffffu, x, o);
+                if (lane >= o) x += t;
+            }
+            incl[g] = x;
+        }
+        __shared__ uint32_t ws[RS_SCAN_VEC][32];
+        if (lane == 31) {
+#pragma unroll
+            for (int g = 0; g < RS_SCAN_VEC; g++) ws[g][warp] = incl[g];
+        }
         __syncthreads();
-        if (warp == 0) {
-            uint32_t w = warp_sums[lane], wi = w;
+        if (warp < RS_SCAN_VEC) { // warp g scans the 32 warp totals of group g
+            uint32_t w = ws[warp][lane], wi = w;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 uint32_t t = __shfl_up_sync(0xffffffffu, wi, o);
                 if (lane >= o) wi += t;
             }
-            warp_sums[lane] = wi - w; // exclusive prefix of the warp totals
-            if (lane == 31) carry_s = carry + wi;
+            ws[warp][lane] = wi - w;
+            if (lane == 31) warp_sums[warp] = wi; // total of group `warp`
         }
         __syncthreads();
-        uint32_t run = carry + warp_sums[warp] + incl - sum;
-        if (i + 3 < total && (total & 3) == 0) {
-            uint4 o4 = make_uint4(run, run + v0, run + v0 + v1, run + v0 + v1 + v2);
-            *reinterpret_cast<uint4*>(hist + i) = o4;
-        } else {
-            if (i < total) hist[i] = run;
-            if (i + 1 < total) hist[i + 1] = run + v0;
-            if (i + 2 < total) hist[i + 2] = run + v0 + v1;
-            if (i + 3 < total) hist[i + 3] = run + v0 + v1 + v2;
+        uint32_t gbase = carry;
+#pragma unroll
+        for (int g = 0; g < RS_SCAN_VEC; g++) {
+            const int i = base + g * 4096 + 4 * tid;
+            uint32_t run = gbase + ws[g][warp] + incl[g] - gsum[g];
+            if (vec_ok && i + 3 < total) {
+                uint4 o4 = make_uint4(run, run + v[g][0], run + v[g][0] + v[g][1], run + v[g][0] + v[g][1] + v[g][2]);
+                *reinterpret_cast<uint4*>(hist + i) = o4;
+            } else {
+                uint32_t r = run;
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    if (i + e < total) hist[i + e] = r;
+                    r += v[g][e];
+                }
+            }
+            gbase += warp_sums[g];
         }
-        __syncthreads(); // warp_sums / carry_s are rewritten by the next tile
+        __syncthreads(); // everyone has read ws / warp_sums / carry_s
+        if (tid == 0) carry_s = gbase;
+        __syncthreads();
     }
 }
 
