@@ -230,18 +230,34 @@ def bench_multi(args, workloads, workload_setup):
     mhz = C.c_double(0)
     _lib.check(L.cf_bench_fp32_peak(C.c_int(local), C.byref(tf), C.byref(mhz)))
 
-    # e2e: every rank round-trips what it owns through pinned host memory each step
+    # e2e: every rank round-trips what it owns through PINNED host memory each step
+    # (D2H particles+counts+ids -> H2D the same -> step), raw C-ABI calls on the pinned buffers
+    cap = int(st.n_owned * 1.2) + 4096
+    pin_p = torch.empty(cap * 44, dtype=torch.uint8).pin_memory()
+    pin_c = torch.zeros(cap, dtype=torch.int32).pin_memory()
+    pin_i = torch.zeros(cap, dtype=torch.int32).pin_memory()
+    cnt = C.c_int(0)
+
+    def round_trip():
+        _lib.check(L.cf_download_particles_ids(sim._h, C.c_void_p(pin_p.data_ptr()), C.c_void_p(pin_c.data_ptr()),
+                                               C.c_void_p(pin_i.data_ptr()), C.c_int(cap), C.byref(cnt)))
+        _lib.check(L.cf_upload_particles_ids(sim._h, C.c_void_p(pin_p.data_ptr()), C.c_void_p(pin_c.data_ptr()),
+                                             C.c_void_p(pin_i.data_ptr()), cnt))
+        return cnt.value
+
     e2e_steps = max(3, min(args.steps, 8))
+    round_trip()
+    one_step()
+    sim.sync()
     barrier()
     t0 = time.perf_counter()
     h2d = d2h = 0
     for _ in range(e2e_steps):
-        p, c, i = sim.downloadOwned()
-        sim.uploadOwned(p, c, i)
+        m = round_trip()
         one_step()
         sim.sync()
-        h2d += len(p) * 52
-        d2h += len(p) * 52
+        h2d += m * 52
+        d2h += m * 52
     barrier()
     e2e_s = all_reduce_max((time.perf_counter() - t0) / e2e_steps)
     h2d = all_reduce_sum(h2d / e2e_steps)
@@ -263,7 +279,7 @@ def bench_multi(args, workloads, workload_setup):
                        "timing": "CUDA events per rank, max over ranks"},
             "e2e": {"value": round(n_total / e2e_s, 1), "unit": METRIC, "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": round(e2e_s * 1e3, 4),
-                    "api": "download owned -> upload owned -> cf_step, every rank, host numpy buffers"},
+                    "api": "cf_download_particles_ids -> cf_upload_particles_ids -> cf_step per rank, pinned host buffers"},
             "gpu_launches": int(launches), "clocks": clocks.summary(),
             "roofline": {"kernel": "pair_force", "bound": "fp32",
                          "achieved": round(37.0 * accepted / (force_ms * 1e-3) * 1e-12, 3) if force_ms > 0 else None,
