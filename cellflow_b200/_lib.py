@@ -115,7 +115,7 @@ SYMBOLS = [
     "cf_update_force_table", "cf_get_force_table", "cf_set_force_table", "cf_set_radio_by_type",
     "cf_set_radio_by_type_value", "cf_get_radio_by_type", "cf_rotate_radio_by_type",
     "cf_init_particles", "cf_upload_particles", "cf_download_particles",
-    "cf_upload_neighbor_counts", "cf_download_neighbor_counts", "cf_move_universe",
+    "cf_upload_neighbor_counts", "cf_download_neighbor_counts", "cf_render_feed", "cf_move_universe",
     "cf_set_params", "cf_get_params", "cf_step", "cf_sync", "cf_step_host", "cf_ratio_with_lfo",
     "cf_build_graph", "cf_download_graph_edges", "cf_download_graph_vertices",
     "cf_default_params", "cf_default_preset", "cf_load_preset", "cf_save_preset",

@@ -225,7 +225,7 @@ static int alloc_particle_buffers(cf_sim* s, int cap) {
     }
     CU(cudaMalloc(&s->frc, c * sizeof(float4)));
     CU(cudaMalloc(&s->d_aos, c * sizeof(AosParticle)));
-    CU(cudaMalloc(&s->d_counts, c * sizeof(int)));
+    CU(cudaMalloc(&s->d_counts, std::max<size_t>(c, 16) * sizeof(int))); // also the render feed's type histogram
     for (int b = 0; b < 2; b++) {
         CU(cudaMemsetAsync(s->pos[b], 0, c * sizeof(float4), s->stream));
         CU(cudaMemsetAsync(s->vel[b], 0, c * sizeof(float4), s->stream));
@@ -826,6 +826,26 @@ extern "C" int cf_download_neighbor_counts(cf_sim* s, int32_t* counts, int count
            oid(s), s->d_aos, s->d_counts, count, 1);
     CU(cudaMemcpyAsync(counts, s->d_counts, sizeof(int) * (size_t)count, cudaMemcpyDeviceToHost, s->stream));
     CU(cudaStreamSynchronize(s->stream));
+    return CF_OK;
+}
+
+extern "C" int cf_render_feed(cf_sim* s, float* xyzt, int capacity, int32_t* type_counts, const void** device_ptr) {
+    ARG(s);
+    ARG(xyzt == nullptr || capacity >= s->n);
+    if (int rc = set_device(s)) return rc;
+    if (device_ptr) *device_ptr = nullptr;
+    if (s->n == 0) {
+        if (type_counts) memset(type_counts, 0, sizeof(int32_t) * s->T);
+        return CF_OK;
+    }
+    // d_aos (44 B per slot) doubles as the float4 output; d_counts holds the T counters
+    float4* out = reinterpret_cast<float4*>(s->d_aos);
+    CU(cudaMemsetAsync(s->d_counts, 0, sizeof(int) * CF_T_MAX, s->stream));
+    LAUNCH(s, render_feed_kernel, div_up(s->n, 256), 256, 0, opos(s), oid(s), s->n, s->slab ? 0 : 1, out, s->d_counts, s->T);
+    if (xyzt) CU(cudaMemcpyAsync(xyzt, out, sizeof(float4) * (size_t)s->n, cudaMemcpyDeviceToHost, s->stream));
+    if (type_counts) CU(cudaMemcpyAsync(type_counts, s->d_counts, sizeof(int) * s->T, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    if (device_ptr) *device_ptr = out; // valid until the next upload / download / render feed call
     return CF_OK;
 }
 

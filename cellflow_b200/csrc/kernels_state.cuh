@@ -172,6 +172,26 @@ __global__ void integrate_kernel(float4* __restrict__ pos4, float4* __restrict__
     frc4[k] = make_float4(ax, ay, az, f.w);
 }
 
+// Render feed (CellFlowWidget::updateParticleBuffer, CellFlowWidget.cpp:742-761, and
+// getParticleTypeCounts, :875-886): (x, y, z, (float)type) per particle in ORIGINAL order plus
+// per-type counts, produced on the device — 16 B per particle instead of the 44-byte AoS round
+// trip and CPU repack the reference does every frame.
+__global__ void render_feed_kernel(const float4* __restrict__ pos4, const int* __restrict__ id, int n, int by_id,
+                                   float4* __restrict__ out, int* __restrict__ type_counts, int T) {
+    __shared__ int hist[CF_T_MAX];
+    if (threadIdx.x < CF_T_MAX) hist[threadIdx.x] = 0;
+    __syncthreads();
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) {
+        float4 p = pos4[k];
+        uint32_t t = __float_as_uint(p.w);
+        out[by_id ? id[k] : k] = make_float4(p.x, p.y, p.z, (float)t);
+        if (t < (uint32_t)T) atomicAdd(&hist[t], 1); // the widget ignores ptype >= numTypes too
+    }
+    __syncthreads();
+    if (threadIdx.x < T && hist[threadIdx.x]) atomicAdd(&type_counts[threadIdx.x], hist[threadIdx.x]);
+}
+
 // Sum of neighbour counts (accepted ordered pairs) for the roofline figure.
 __global__ void sum_counts_kernel(const float4* __restrict__ frc4, int n, unsigned long long* out) {
     unsigned long long local = 0;

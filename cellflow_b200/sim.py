@@ -214,6 +214,15 @@ class ParticleSimulation:
                                    C.c_void_p(cin[0]), C.c_void_p(pout[0]), C.c_void_p(cout[0]),
                                    C.c_int(pin[1])))
 
+    def getRenderFeed(self):
+        """(xyzt[n,4], type_counts[T]): the widget's per-frame vertex data and type histogram
+        (CellFlowWidget.cpp:742-761, 875-886), built on the device."""
+        n, T = self.getParticleCount(), self.getNumParticleTypes()
+        xyzt = np.zeros((n, 4), dtype=np.float32)
+        counts = np.zeros(T, dtype=np.int32)
+        check(self._L.cf_render_feed(self._h, _p(xyzt), C.c_int(n), _p(counts), None))
+        return xyzt, counts
+
     # -- multi-GPU slabs (one process per GPU) ----------------------------------------------------
     def commInit(self, rank: int, world: int, nccl_id: bytes | None, capacity: int):
         """Rank `rank` of `world` owns x in [rank*W/world, (rank+1)*W/world).  world == 1 runs the

@@ -180,6 +180,12 @@ int cf_download_particles(cf_sim* sim, cf_particle* aos, int count);
 /* neighborCounts ping-pong buffer of the last step (.cu:544-545, 165), original order. */
 int cf_upload_neighbor_counts(cf_sim* sim, const int32_t* counts, int count);
 int cf_download_neighbor_counts(cf_sim* sim, int32_t* counts, int count);
+/* Render feed: what CellFlowWidget::updateParticleBuffer (CellFlowWidget.cpp:742-761) builds on the
+ * CPU from getParticleData every frame — (x, y, z, (float)type) per particle, original order
+ * (slot order in slab mode) — plus the per-type counts of getParticleTypeCounts (:875-886).
+ * xyzt: capacity*4 floats on the host or NULL; type_counts: numParticleTypes ints or NULL;
+ * device_ptr: receives a device pointer to the same float4 stream (zero-copy consumers) or NULL. */
+int cf_render_feed(cf_sim* sim, float* xyzt, int capacity, int32_t* type_counts, const void** device_ptr);
 /* updateCanvasDimensions / moveUniverse, .cu:507-511, 585-592. */
 int cf_move_universe(cf_sim* sim, float dx, float dy, float dz);
 

@@ -336,3 +336,17 @@ def test_empty_and_degenerate_inputs():
     with pytest.raises(cf.CellFlowError):
         sim.setParticleData(np.zeros(10, cf.PARTICLE)[:0], None) if False else sim.setOption("nope", 1)
     sim.close()
+
+
+def test_render_feed_matches_widget_packing():
+    """(x, y, z, float(type)) in particle order + per-type counts, as CellFlowWidget builds them
+    on the CPU from getParticleData (CellFlowWidget.cpp:742-761, 875-886)."""
+    p, table, radio = U.config("pulser")
+    state, counts = U.random_state(7777, 6, 12, p.canvas, "cube")
+    sim = make_sim(p, table, radio, state, counts)
+    sim.simulate(steps=2)
+    now = sim.getParticleData()
+    xyzt, tc = sim.getRenderFeed()
+    assert np.array_equal(xyzt[:, :3], now["pos"]) and np.array_equal(xyzt[:, 3], now["ptype"].astype(np.float32))
+    assert np.array_equal(tc, np.bincount(now["ptype"], minlength=6))
+    sim.close()
