@@ -25,6 +25,7 @@
 #include "kernels_sort.cuh"
 #include "kernels_state.cuh"
 #include "kernels_tile.cuh"
+#include "kernels_tile4.cuh"
 #include "nccl_dyn.h"
 
 static_assert(sizeof(AosParticle) == 44 && sizeof(cf_particle) == 44, "reference Particle is 44 B");
@@ -115,6 +116,15 @@ struct cf_sim {
     size_t tiles_cap = 0;
     int* d_tile_ctrl = nullptr;
     float* d_half = nullptr;      // per-type conservative half radius (non-uniform radii)
+    // generation-4 tile kernel, per-type radii: j copy sorted by (xy row, type, z cell, Morton)
+    uint32_t* hk[2] = {nullptr, nullptr};
+    uint32_t* hv[2] = {nullptr, nullptr};
+    int* h_cell_of = nullptr;
+    float4* h_pos = nullptr;
+    uint32_t* h_comp = nullptr;
+    size_t homog_cap = 0;
+    int* h_start = nullptr;
+    size_t h_start_cap = 0;
     bool half_bound_ok = true;
     int sm_count = 148;
 
@@ -153,7 +163,7 @@ struct cf_sim {
 
     // options
     int opt_stencil = 0;     // reserved (0 = automatic)
-    int opt_force_kernel = 0; // 0 auto, 1 per-particle, 2 tile
+    int opt_force_kernel = 0; // 0 auto, 1 per-particle, 2 tile (generation 3), 3 tile (generation 4)
     int opt_timing = 0;
     double opt_max_cells_per_particle = 16.0; // fine grids pay off for clustered states (cells are cheap)
 
@@ -612,6 +622,14 @@ extern "C" int cf_destroy(cf_sim* s) {
     cudaFree(s->gstart);
     cudaFree(s->d_tile_ctrl);
     cudaFree(s->d_half);
+    for (int b = 0; b < 2; b++) {
+        cudaFree(s->hk[b]);
+        cudaFree(s->hv[b]);
+    }
+    cudaFree(s->h_cell_of);
+    cudaFree(s->h_pos);
+    cudaFree(s->h_comp);
+    cudaFree(s->h_start);
     for (auto& ev : s->ev_pool)
         for (int i = 0; i < 6; i++) cudaEventDestroy(ev.e[i]);
     if (s->ev_g0) cudaEventDestroy(s->ev_g0);
@@ -897,18 +915,65 @@ static StepEvents* next_events(cf_sim* s) {
     return &s->ev_pool[s->ev_used++];
 }
 
+// Builds the type-homogeneous j copy for the generation-4 tile kernel (per-type radii): one
+// stable sort of the cell-sorted slots on key = row * T + type, a gather and a bounds pass.
+static int build_homog_copy(cf_sim* s) {
+    const int nz = s->sc.dims[2];
+    const int nrow = s->ncell / nz;
+    const int nslots = s->slab ? std::min(s->cap, s->base + s->n + s->cap_halo) : s->n;
+    const int nkeys = nrow * s->T * nz; // composite keys (row * T + type) * nz + cz
+    if ((size_t)nslots > s->homog_cap) {
+        CU(cudaStreamSynchronize(s->stream));
+        for (int b = 0; b < 2; b++) {
+            cudaFree(s->hk[b]);
+            cudaFree(s->hv[b]);
+            s->hk[b] = s->hv[b] = nullptr;
+        }
+        cudaFree(s->h_cell_of);
+        cudaFree(s->h_pos);
+        cudaFree(s->h_comp);
+        s->h_cell_of = nullptr, s->h_pos = nullptr, s->h_comp = nullptr;
+        s->homog_cap = (size_t)nslots + (size_t)nslots / 8 + 1024;
+        for (int b = 0; b < 2; b++) {
+            CU(cudaMalloc(&s->hk[b], s->homog_cap * sizeof(uint32_t)));
+            CU(cudaMalloc(&s->hv[b], s->homog_cap * sizeof(uint32_t)));
+        }
+        CU(cudaMalloc(&s->h_cell_of, s->homog_cap * sizeof(int)));
+        CU(cudaMalloc(&s->h_pos, s->homog_cap * sizeof(float4)));
+        CU(cudaMalloc(&s->h_comp, s->homog_cap * sizeof(uint32_t)));
+    }
+    if ((size_t)nkeys + 2 > s->h_start_cap) {
+        CU(cudaStreamSynchronize(s->stream));
+        cudaFree(s->h_start);
+        s->h_start = nullptr;
+        s->h_start_cap = (size_t)nkeys + 2 + (size_t)nkeys / 4;
+        CU(cudaMalloc(&s->h_start, s->h_start_cap * sizeof(int)));
+    }
+    const float4* pos = s->pos[s->cur];
+    LAUNCH(s, homog_key_kernel, div_up(nslots, 256), 256, 0, pos, s->cell_start, s->ncell, nz, s->T, nslots, s->hk[0],
+           s->hv[0], s->h_cell_of);
+    int src = 0;
+    if (int rc = radix_sort_pairs(s, s->hk, s->hv, nslots, (long long)nrow * s->T + 1, &src)) return rc;
+    LAUNCH(s, homog_gather_kernel, div_up(nslots, 256), 256, 0, s->hk[src], s->hv[src], pos, s->h_cell_of, nz, nslots,
+           s->h_pos, s->h_comp);
+    LAUNCH(s, homog_bounds_kernel, div_up(nkeys + 1, 256), 256, 0, s->h_comp, nslots, s->h_start, nkeys);
+    return 0;
+}
+
 static int launch_force(cf_sim* s) {
     int n = s->n;
     const float4* pos = s->pos[s->cur];
     int kernel = s->opt_force_kernel;
     const int global_nx = s->slab ? s->nxl * s->world : s->sc.dims[0];
-    const bool wrap_ok = s->sc.dims[1] >= 4 && s->sc.dims[2] >= 4 && global_nx >= 4 &&
-                         (s->sc.uniform_radius || s->half_bound_ok);
+    // the tile kernels decide the minimum-image wrap per neighbour cell: >= 4 cells per periodic axis
+    const bool wrap_ok = s->sc.dims[1] >= 4 && s->sc.dims[2] >= 4 && global_nx >= 4;
+    const bool v3_ok = wrap_ok && (s->sc.uniform_radius || s->half_bound_ok);
     bool tile_ok = wrap_ok && tile_kernel_applicable(s->sc, n, s->ncell);
-    if (kernel == 0) kernel = tile_ok ? 2 : 1;
-    if (kernel == 2 && !wrap_ok) kernel = 1; // the tile kernel's per-run wrap needs >= 4 cells per periodic axis
+    if (kernel == 0) kernel = tile_ok ? 3 : 1;
+    if (kernel == 3 && !wrap_ok) kernel = 1;
+    if (kernel == 2 && !v3_ok) kernel = 1;
     s->last_force_kernel = kernel;
-    if (kernel == 2) {
+    if (kernel == 2 || kernel == 3) {
         size_t need = (size_t)s->ncell + (size_t)n / TK_TI + 2;
         if (need > s->tiles_cap) {
             CU(cudaStreamSynchronize(s->stream));
@@ -917,12 +982,22 @@ static int launch_force(cf_sim* s) {
             s->tiles_cap = need + need / 4;
             CU(cudaMalloc(&s->d_tiles, s->tiles_cap * sizeof(int2)));
         }
+        const bool homog = kernel == 3 && !s->sc.uniform_radius;
+        if (homog)
+            if (int rc = build_homog_copy(s)) return rc;
         CU(cudaMemsetAsync(s->d_tile_ctrl, 0, 2 * sizeof(int), s->stream));
         LAUNCH(s, build_tiles_kernel, div_up(s->ncell, 256), 256, 0, s->cell_start, s->ncell, s->sc.x_off,
                s->sc.x_off + s->sc.x_cells - 1,
                s->sc.dims[1] * s->sc.dims[2], s->d_tiles, s->d_tile_ctrl);
         int grid = s->sm_count * 4;
-        if (s->sc.uniform_radius)
+        if (kernel == 3) {
+            if (homog)
+                LAUNCH(s, force_tile4_kernel<1>, grid, T4_WARPS * 32, 0, pos, s->cell_start, s->h_pos, s->h_start,
+                       s->d_tiles, s->d_tile_ctrl, s->frc, s->sc, s->d_tables);
+            else
+                LAUNCH(s, force_tile4_kernel<0>, grid, T4_WARPS * 32, 0, pos, s->cell_start, pos, s->cell_start,
+                       s->d_tiles, s->d_tile_ctrl, s->frc, s->sc, s->d_tables);
+        } else if (s->sc.uniform_radius)
             LAUNCH(s, force_tile_kernel<true>, grid, TK_THREADS, 0, pos, s->cell_start, s->d_tiles, s->d_tile_ctrl,
                    s->frc, s->sc, s->d_tables, 0.f, s->d_half);
         else
@@ -959,7 +1034,8 @@ static std::vector<char> step_signature(const cf_sim* s) {
     put(&s->sc, sizeof(s->sc));
     const void* ptrs[] = {s->pos[0], s->pos[1], s->vel[0], s->vel[1], s->id[0], s->id[1], s->frc, s->keys[0],
                           s->keys[1], s->vals[0], s->vals[1], s->hist, s->cell_start, s->d_tiles, s->d_tile_ctrl,
-                          s->d_tables, s->d_half};
+                          s->d_tables, s->d_half, s->hk[0], s->hk[1], s->hv[0], s->hv[1], s->h_cell_of, s->h_pos,
+                          s->h_comp, s->h_start};
     put(ptrs, sizeof(ptrs));
     int ints[] = {s->n, s->ncell, s->cur, s->opt_force_kernel, s->sorted_valid ? 1 : 0, s->half_bound_ok ? 1 : 0};
     put(ints, sizeof(ints));

@@ -1,0 +1,472 @@
+// kernels_tile4.cuh — pair-force kernel, generation 4 (the FP32-bound hot kernel).
+//
+// Same decomposition as kernels_tile.cuh (one WARP owns a tile of <= 128 particles of one cell as
+// 4 register-resident layers of 32; the 27 neighbour cells are streamed as <= 18 contiguous runs
+// through a warp-private double buffer, 64 j per chunk; one warp vote per (layer, quad of 4 j)
+// gates the force terms), with what the round-1 ncu captures asked for
+// (profiles/r01_force_kernel_history.md, profiles/r02_force_kernel.md):
+//
+//   * BOX PREFILTER.  The exact test of a (layer, quad) block costs 12 packed FP32 instructions
+//     = 24 FMA-pipe cycles per SM sub-partition, and 50-70% of the blocks are dead.  Per chunk
+//     the 64 (layer, quad) combinations are tested lane-parallel, bounding box of the layer's
+//     32 i against bounding box of the quad's 4 j (2 evaluations per lane + 2 ballots); only
+//     combinations whose boxes come within the cut-off run the exact test.  Quads with no live
+//     layer are not even loaded.
+//   * TYPE-HOMOGENEOUS j RUNS for per-type radii (MODE 1).  The j stream comes from a second
+//     copy of the positions sorted by (xy row, type, z cell, Morton): inside a sub-run every j
+//     has the same type, so cut2 / force value / 1/Reff of a pair depend on the lane only and
+//     are fetched once per sub-run instead of once per pair; the vote test is the exact accept
+//     test.  The v3 kernel needed a float4 table gather and a second compare per evaluated pair.
+//   * LEANER FORCE PATH.  Accept bits as integer masks (set.lt.s32.f32): the neighbour count is
+//     two IADD3, the rejected pairs are zeroed with one AND on the bits of s (so a NaN/Inf of a
+//     padded or rejected pair can never leak); no generic-pointer arithmetic on shared memory.
+//   * one code path for every tile occupancy (empty layers have empty boxes and are never live)
+//     and prefetch across run boundaries.
+//
+// Exactness is unchanged: displacement = (jx + (-px)) [+ s], s in {-W, 0, +W} per run (exact,
+// see kernels_tile.cuh), d2 = fma(dz,dz, fma(dx,dx, dy*dy)), accept <=> d2 < cut2[ti][tj].
+// The box prefilter is conservative (margin 1e-4 relative + 0.01 absolute on the squared gap).
+#pragma once
+#include "kernels_tile.cuh"
+
+#define T4_WARPS 4
+#define T4_JC 64
+#define T4_MAXSUB (TK_MAX_RUNS * CF_T_MAX)
+#define T4_INF __int_as_float(0x7f800000)
+
+template <int MODE>
+struct T4Shared {
+    float x[T4_WARPS][2][T4_JC];
+    float y[T4_WARPS][2][T4_JC];
+    float z[T4_WARPS][2][T4_JC];
+    int t[T4_WARPS][2][T4_JC];                       // MODE 0: byte offset of j's row in s_fv
+    int2 sub[T4_WARPS][MODE ? T4_MAXSUB : TK_MAX_RUNS]; // [j0, j1) of every (sub-)run
+    float4 cst[MODE ? T4_WARPS : 1][4][32];          // MODE 1: (c2, A, B, -) of (layer, lane) for the current sub-run
+};
+
+__device__ __forceinline__ int t4_setlt(float a, float b) { // 0xffffffff if a < b else 0
+    int r;
+    asm("set.lt.s32.f32 %0, %1, %2;" : "=r"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ float t4_and(float v, int m) { return __int_as_float(__float_as_int(v) & m); }
+
+// order-preserving float <-> uint map (for REDUX.MIN/MAX on floats)
+__device__ __forceinline__ unsigned t4_f2o(float f) {
+    unsigned u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float t4_o2f(unsigned u) {
+    return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+__device__ __forceinline__ float t4_warp_min(float f) { return t4_o2f(__reduce_min_sync(0xffffffffu, t4_f2o(f))); }
+__device__ __forceinline__ float t4_warp_max(float f) { return t4_o2f(__reduce_max_sync(0xffffffffu, t4_f2o(f))); }
+
+__device__ __forceinline__ float t4_lds(unsigned addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+
+// Force terms of the 4 pairs of one (layer, quad) block for one lane.
+//   s = fv * (rep * e / dist - att / Reff),  e = exp2(c2 * x),  x = d2 + 1e-4,  1/dist = rsqrt(x)
+// MODE 0: c2, nb = -att/Reff are kernel constants, fv comes from the transposed table in shared
+// memory; MODE 1: c2, A = fv * rep, B = -fv * att / Reff are per (lane, layer) constants of the
+// current sub-run.  Rejected pairs: the bits of s are ANDed with the accept mask.
+template <int MODE>
+__device__ __forceinline__ void t4_live(u64 dxa, u64 dya, u64 dza, u64 d2a, u64 dxb, u64 dyb, u64 dzb, u64 d2b,
+                                        float a0, float a1, float b0, float b1, float thr, float c2, float pa,
+                                        float pb, unsigned fv_base, int4 Tq, u64& ax, u64& ay, u64& az, int& cnt) {
+    const int m0 = t4_setlt(a0, thr), m1 = t4_setlt(a1, thr), m2 = t4_setlt(b0, thr), m3 = t4_setlt(b1, thr);
+    const u64 eps = tk_pack(0.0001f, 0.0001f);
+    const u64 xa = tk_add2(d2a, eps), xb = tk_add2(d2b, eps);
+    const u64 c22 = tk_pack(c2, c2);
+    float ta0, ta1, tb0, tb1, xa0, xa1, xb0, xb1;
+    tk_unpack(tk_mul2(xa, c22), ta0, ta1);
+    tk_unpack(tk_mul2(xb, c22), tb0, tb1);
+    tk_unpack(xa, xa0, xa1);
+    tk_unpack(xb, xb0, xb1);
+    const u64 era = tk_mul2(tk_pack(cf_ex2(ta0), cf_ex2(ta1)), tk_pack(cf_rsqrt(xa0), cf_rsqrt(xa1)));
+    const u64 erb = tk_mul2(tk_pack(cf_ex2(tb0), cf_ex2(tb1)), tk_pack(cf_rsqrt(xb0), cf_rsqrt(xb1)));
+    u64 sa = tk_fma2(era, tk_pack(pa, pa), tk_pack(pb, pb));
+    u64 sb = tk_fma2(erb, tk_pack(pa, pa), tk_pack(pb, pb));
+    if (MODE == 0) {
+        const float f0 = t4_lds(fv_base + Tq.x), f1 = t4_lds(fv_base + Tq.y);
+        const float f2 = t4_lds(fv_base + Tq.z), f3 = t4_lds(fv_base + Tq.w);
+        sa = tk_mul2(sa, tk_pack(f0, f1));
+        sb = tk_mul2(sb, tk_pack(f2, f3));
+    }
+    float s0, s1, s2, s3;
+    tk_unpack(sa, s0, s1);
+    tk_unpack(sb, s2, s3);
+    sa = tk_pack(t4_and(s0, m0), t4_and(s1, m1));
+    sb = tk_pack(t4_and(s2, m2), t4_and(s3, m3));
+    cnt -= (m0 + m1) + (m2 + m3);
+    ax = tk_fma2(sb, dxb, tk_fma2(sa, dxa, ax));
+    ay = tk_fma2(sb, dyb, tk_fma2(sa, dya, ay));
+    az = tk_fma2(sb, dzb, tk_fma2(sa, dza, az));
+}
+
+// All live (layer, quad) blocks of one staged chunk.
+template <int MODE, bool WRAP>
+__device__ __forceinline__ void t4_chunk(const float* __restrict__ xs, const float* __restrict__ ys,
+                                         const float* __restrict__ zs, const int* __restrict__ ts, int nquads,
+                                         unsigned mask0, unsigned mask1, const float (&npx)[TK_IPT],
+                                         const float (&npy)[TK_IPT], const float (&npz)[TK_IPT],
+                                         const float (&thr)[TK_IPT], const unsigned (&fvb)[TK_IPT],
+                                         const float4* __restrict__ cst, float sx, float sy, float sz, float c2u,
+                                         float pau, float pbu, u64 (&ax)[TK_IPT], u64 (&ay)[TK_IPT],
+                                         u64 (&az)[TK_IPT], int (&cnt)[TK_IPT]) {
+    const u64 sx2 = tk_pack(sx, sx), sy2 = tk_pack(sy, sy), sz2 = tk_pack(sz, sz);
+#pragma unroll 1
+    for (int q = 0; q < nquads; q++) {
+        const unsigned m4 = (((q & 8) ? mask1 : mask0) >> ((q & 7) << 2)) & 15u;
+        if (m4 == 0u) continue; // no layer's box comes near this quad's box
+        const float4 X = *reinterpret_cast<const float4*>(xs + 4 * q);
+        const float4 Y = *reinterpret_cast<const float4*>(ys + 4 * q);
+        const float4 Z = *reinterpret_cast<const float4*>(zs + 4 * q);
+        int4 Tq = make_int4(0, 0, 0, 0);
+        if (MODE == 0) Tq = *reinterpret_cast<const int4*>(ts + 4 * q);
+        const u64 xa = tk_pack(X.x, X.y), xb = tk_pack(X.z, X.w);
+        const u64 ya = tk_pack(Y.x, Y.y), yb = tk_pack(Y.z, Y.w);
+        const u64 za = tk_pack(Z.x, Z.y), zb = tk_pack(Z.z, Z.w);
+#pragma unroll
+        for (int k = 0; k < TK_IPT; k++) {
+            if (!(m4 & (1u << k))) continue; // warp-uniform
+            const u64 px = tk_pack(npx[k], npx[k]), py = tk_pack(npy[k], npy[k]), pz = tk_pack(npz[k], npz[k]);
+            u64 dxa = tk_add2(xa, px), dxb = tk_add2(xb, px);
+            u64 dya = tk_add2(ya, py), dyb = tk_add2(yb, py);
+            u64 dza = tk_add2(za, pz), dzb = tk_add2(zb, pz);
+            if (WRAP) {
+                dxa = tk_add2(dxa, sx2), dxb = tk_add2(dxb, sx2);
+                dya = tk_add2(dya, sy2), dyb = tk_add2(dyb, sy2);
+                dza = tk_add2(dza, sz2), dzb = tk_add2(dzb, sz2);
+            }
+            const u64 d2a = tk_fma2(dza, dza, tk_fma2(dxa, dxa, tk_mul2(dya, dya)));
+            const u64 d2b = tk_fma2(dzb, dzb, tk_fma2(dxb, dxb, tk_mul2(dyb, dyb)));
+            float a0, a1, b0, b1;
+            tk_unpack(d2a, a0, a1);
+            tk_unpack(d2b, b0, b1);
+            const float mn = fminf(fminf(a0, a1), fminf(b0, b1));
+            if (__any_sync(0xffffffffu, mn < thr[k])) {
+                float c2 = c2u, pa = pau, pb = pbu;
+                if (MODE == 1) {
+                    const float4 cs = cst[k * 32];
+                    c2 = cs.x, pa = cs.y, pb = cs.z;
+                }
+                t4_live<MODE>(dxa, dya, dza, d2a, dxb, dyb, dzb, d2b, a0, a1, b0, b1, thr[k], c2, pa, pb, fvb[k], Tq,
+                              ax[k], ay[k], az[k], cnt[k]);
+            }
+        }
+    }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(T4_WARPS * 32, 4)
+force_tile4_kernel(const float4* __restrict__ pos4, const int* __restrict__ cell_start,
+                   const float4* __restrict__ posj, const int* __restrict__ startj,
+                   const int2* __restrict__ tiles, int* __restrict__ ctrl, float4* __restrict__ frc4, StepConst c,
+                   const DeviceTables* __restrict__ tables) {
+    __shared__ __align__(16) T4Shared<MODE> sm;
+    // MODE 0: s_tab[tj*T + ti] = fv.  MODE 1: s_tab4[tj*T + ti] = (c2, fv*rep, -fv*att/Reff, cut2)
+    __shared__ __align__(16) float s_tab[CF_TT_MAX * (MODE ? 4 : 1)];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int T = c.T;
+    for (int i = tid; i < T * T; i += blockDim.x) {
+        const int ti = i / T, tj = i % T; // tables are [ti][tj]
+        if (MODE == 0) {
+            s_tab[tj * T + ti] = tables->force[i];
+        } else {
+            const float inv = tables->inv_reff[i], fv = tables->force[i];
+            float* e = &s_tab[(tj * T + ti) * 4];
+            e[0] = c.nk_log2e * inv * inv;
+            e[1] = fv * c.repulsion;
+            e[2] = -(fv * (c.attraction * inv));
+            e[3] = tables->cut2[i];
+        }
+    }
+    __syncthreads(); // the only block-level barrier: tables are read-only afterwards
+    const int ntiles = ctrl[0];
+    const int ny = c.dims[1], nz = c.dims[2];
+    const float cutu = c.cut2_uniform;
+    const float c2u = c.nk_log2e * c.inv_reff_uniform * c.inv_reff_uniform;
+    const float pau = c.repulsion, pbu = -(c.attraction * c.inv_reff_uniform);
+    float* const wx = &sm.x[warp][0][0];
+    float* const wy = &sm.y[warp][0][0];
+    float* const wz = &sm.z[warp][0][0];
+    int* const wt = &sm.t[warp][0][0];
+    int2* const wsub = &sm.sub[warp][0];
+    float4* const wcst = &sm.cst[MODE ? warp : 0][0][lane];
+    const unsigned s_tab_addr = (unsigned)__cvta_generic_to_shared(s_tab);
+    const int kk = lane & 3; // the layer this lane tests in the box prefilter
+
+    for (;;) {
+        int tile = 0;
+        if (lane == 0) tile = atomicAdd(&ctrl[1], 1);
+        tile = __shfl_sync(0xffffffffu, tile, 0);
+        if (tile >= ntiles) break;
+        const int2 tl = tiles[tile];
+        const int cell = tl.x;
+        const int cz = cell % nz, cy = (cell / nz) % ny, cx = cell / (nz * ny);
+        const int i_begin = cell_start[cell] + tl.y * TK_TI;
+        const int ni = min(cell_start[cell + 1] - i_begin, TK_TI);
+
+        // ---- neighbour runs: lane r < 18 holds run r = (row r/2 of the 3x3 (x,y) rows, z segment r%2)
+        float r_sx = 0.f, r_sy = 0.f, r_sz = 0.f; // minimum-image shift of the run: -W, 0 or +W per axis
+        int r_row = -1, r_z0 = 0, r_z1 = 0;
+        if (lane < TK_MAX_RUNS) {
+            int rho = lane >> 1, seg = lane & 1;
+            int x = cx + rho / 3 - 1, y = cy + rho % 3 - 1;
+            bool valid = true;
+            if (c.periodic_x) {
+                if (x < 0) { x = c.dims[0] - 1; r_sx = -c.W[0]; } else if (x >= c.dims[0]) { x = 0; r_sx = c.W[0]; }
+            } else { // slab mode: i-cells are layers 1..dims-2, so x stays inside [0, dims-1]
+                if (x < 0 || x >= c.dims[0]) valid = false;
+                else if (x == 0) r_sx = c.gshift_lo;
+                else if (x == c.dims[0] - 1) r_sx = c.gshift_hi;
+            }
+            if (y < 0) { y = ny - 1; r_sy = -c.W[1]; } else if (y >= ny) { y = 0; r_sy = c.W[1]; }
+            if (seg == 0) {
+                r_z0 = max(cz - 1, 0);
+                r_z1 = min(cz + 1, nz - 1);
+            } else if (cz == 0) {
+                r_z0 = r_z1 = nz - 1;
+                r_sz = -c.W[2];
+            } else if (cz == nz - 1) {
+                r_z0 = r_z1 = 0;
+                r_sz = c.W[2];
+            } else {
+                valid = false;
+            }
+            if (valid) r_row = x * ny + y;
+        }
+        // (sub-)run list in shared memory: MODE 0 entry r = run r; MODE 1 entry r*T + t = type t of run r
+        // 2 bits per axis: 1 = -W, 2 = +W
+        const int r_code = (r_sx < 0.f ? 1 : (r_sx > 0.f ? 2 : 0)) | (r_sy < 0.f ? 4 : (r_sy > 0.f ? 8 : 0)) |
+                           (r_sz < 0.f ? 16 : (r_sz > 0.f ? 32 : 0));
+        __syncwarp();
+        const int nsub = MODE ? TK_MAX_RUNS * T : TK_MAX_RUNS;
+        for (int e0 = 0; e0 < nsub; e0 += 32) {
+            const int e = e0 + lane;
+            const int r = MODE ? e / T : e, t = MODE ? e % T : 0;
+            const int row = __shfl_sync(0xffffffffu, r_row, r & 31);
+            const int z0 = __shfl_sync(0xffffffffu, r_z0, r & 31), z1 = __shfl_sync(0xffffffffu, r_z1, r & 31);
+            if (e < nsub) {
+                int2 jj = make_int2(0, 0);
+                if (row >= 0) {
+                    const int b = MODE ? (row * T + t) * nz : row * nz;
+                    jj.x = startj[b + z0];
+                    jj.y = startj[b + z1 + 1];
+                }
+                wsub[e] = jj;
+            }
+        }
+        __syncwarp();
+
+        // ---- my i particles: layer k holds slots i_begin + 32k + lane ----
+        float npx[TK_IPT], npy[TK_IPT], npz[TK_IPT], thr[TK_IPT];
+        unsigned fvb[TK_IPT]; // MODE 0: shared address of s_tab[ti] (MODE 1: unused)
+        unsigned tis = 0;     // the 4 types of this lane's particles, 4 bits each
+        u64 ax[TK_IPT], ay[TK_IPT], az[TK_IPT];
+        int cnt[TK_IPT];
+        float blo[3], bhi[3]; // bounding box of layer kk
+        blo[0] = blo[1] = blo[2] = T4_INF;
+        bhi[0] = bhi[1] = bhi[2] = -T4_INF;
+#pragma unroll
+        for (int k = 0; k < TK_IPT; k++) {
+            const int il = k * 32 + lane;
+            const bool v = il < ni;
+            const float4 p = v ? pos4[i_begin + il] : make_float4(-TK_FAR, -TK_FAR, -TK_FAR, 0.f);
+            const int ti = v ? (int)__float_as_uint(p.w) : 0;
+            npx[k] = -p.x, npy[k] = -p.y, npz[k] = -p.z;
+            fvb[k] = MODE ? 0u : s_tab_addr + (unsigned)(ti * 4);
+            tis |= (unsigned)ti << (4 * k);
+            thr[k] = MODE ? 0.f : (v ? cutu : 0.f);
+            ax[k] = ay[k] = az[k] = tk_pack(0.f, 0.f);
+            cnt[k] = 0;
+            const float lx = t4_warp_min(v ? p.x : T4_INF), hx = t4_warp_max(v ? p.x : -T4_INF);
+            const float ly = t4_warp_min(v ? p.y : T4_INF), hy = t4_warp_max(v ? p.y : -T4_INF);
+            const float lz = t4_warp_min(v ? p.z : T4_INF), hz = t4_warp_max(v ? p.z : -T4_INF);
+            if (kk == k) blo[0] = lx, blo[1] = ly, blo[2] = lz, bhi[0] = hx, bhi[1] = hy, bhi[2] = hz;
+        }
+        float thrA = MODE ? 0.f : cutu * 1.0001f + 0.01f; // prefilter threshold of layer kk (squared box gap)
+
+        // ---- stream the chunks of all (sub-)runs, prefetching across run boundaries ----
+        int si = -1, off = 0, end = 0; // prefetch cursor
+        bool have;
+#define T4_ADVANCE()                                \
+    do {                                            \
+        off += T4_JC;                               \
+        have = true;                                \
+        while (off >= end) {                        \
+            if (++si >= nsub) { have = false; break; } \
+            const int2 e_ = wsub[si];               \
+            off = e_.x, end = e_.y;                 \
+        }                                           \
+    } while (0)
+        T4_ADVANCE();
+        float4 q0 = make_float4(TK_FAR, TK_FAR, TK_FAR, 0.f), q1 = q0;
+        if (have && off + lane < end) q0 = posj[off + lane];
+        if (have && off + 32 + lane < end) q1 = posj[off + 32 + lane];
+        int cur_si = -1, buf = 0;
+        float sx = 0.f, sy = 0.f, sz = 0.f;
+        bool wrap = false;
+        while (have) {
+            const int csi = si, coff = off, cend = end;
+            // publish the prefetched chunk
+            float* bx = wx + buf * T4_JC;
+            float* by = wy + buf * T4_JC;
+            float* bz = wz + buf * T4_JC;
+            int* bt = wt + buf * T4_JC;
+            bx[lane] = q0.x, by[lane] = q0.y, bz[lane] = q0.z;
+            bx[lane + 32] = q1.x, by[lane + 32] = q1.y, bz[lane + 32] = q1.z;
+            if (MODE == 0) {
+                bt[lane] = (int)__float_as_uint(q0.w) * (T * 4);
+                bt[lane + 32] = (int)__float_as_uint(q1.w) * (T * 4);
+            }
+            // bounding boxes of the quads: 4 consecutive lanes hold one quad of each half
+            const bool v0 = coff + lane < cend, v1 = coff + 32 + lane < cend;
+            float l0x = v0 ? q0.x : T4_INF, l0y = v0 ? q0.y : T4_INF, l0z = v0 ? q0.z : T4_INF;
+            float h0x = v0 ? q0.x : -T4_INF, h0y = v0 ? q0.y : -T4_INF, h0z = v0 ? q0.z : -T4_INF;
+            float l1x = v1 ? q1.x : T4_INF, l1y = v1 ? q1.y : T4_INF, l1z = v1 ? q1.z : T4_INF;
+            float h1x = v1 ? q1.x : -T4_INF, h1y = v1 ? q1.y : -T4_INF, h1z = v1 ? q1.z : -T4_INF;
+#pragma unroll
+            for (int o = 1; o <= 2; o <<= 1) {
+                l0x = fminf(l0x, __shfl_xor_sync(0xffffffffu, l0x, o));
+                l0y = fminf(l0y, __shfl_xor_sync(0xffffffffu, l0y, o));
+                l0z = fminf(l0z, __shfl_xor_sync(0xffffffffu, l0z, o));
+                h0x = fmaxf(h0x, __shfl_xor_sync(0xffffffffu, h0x, o));
+                h0y = fmaxf(h0y, __shfl_xor_sync(0xffffffffu, h0y, o));
+                h0z = fmaxf(h0z, __shfl_xor_sync(0xffffffffu, h0z, o));
+                l1x = fminf(l1x, __shfl_xor_sync(0xffffffffu, l1x, o));
+                l1y = fminf(l1y, __shfl_xor_sync(0xffffffffu, l1y, o));
+                l1z = fminf(l1z, __shfl_xor_sync(0xffffffffu, l1z, o));
+                h1x = fmaxf(h1x, __shfl_xor_sync(0xffffffffu, h1x, o));
+                h1y = fmaxf(h1y, __shfl_xor_sync(0xffffffffu, h1y, o));
+                h1z = fmaxf(h1z, __shfl_xor_sync(0xffffffffu, h1z, o));
+            }
+            __syncwarp();
+            // prefetch the next chunk (possibly of the next run) while this one is processed
+            T4_ADVANCE();
+            q0 = make_float4(TK_FAR, TK_FAR, TK_FAR, 0.f);
+            q1 = q0;
+            if (have && off + lane < end) q0 = posj[off + lane];
+            if (have && off + 32 + lane < end) q1 = posj[off + 32 + lane];
+
+            if (csi != cur_si) { // a new (sub-)run: its minimum-image shift, MODE 1: its pair constants
+                cur_si = csi;
+                const int r = MODE ? csi / T : csi;
+                const int code = __shfl_sync(0xffffffffu, r_code, r);
+                sx = (code & 1) ? -c.W[0] : ((code & 2) ? c.W[0] : 0.f);
+                sy = (code & 4) ? -c.W[1] : ((code & 8) ? c.W[1] : 0.f);
+                sz = (code & 16) ? -c.W[2] : ((code & 32) ? c.W[2] : 0.f);
+                wrap = code != 0;
+                if (MODE == 1) {
+                    const int tj = csi - r * T;
+                    const char* row = reinterpret_cast<const char*>(s_tab) + tj * (T * 16);
+                    float tA = 0.f;
+#pragma unroll
+                    for (int k = 0; k < TK_IPT; k++) {
+                        const float4 e = *reinterpret_cast<const float4*>(row + ((tis >> (4 * k)) & 15u) * 16u);
+                        const bool v = k * 32 + lane < ni;
+                        thr[k] = v ? e.w : 0.f;
+                        wcst[k * 32] = make_float4(e.x, e.y, e.z, 0.f);
+                        const float mx = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(thr[k]))); // thr >= 0
+                        if (kk == k) tA = mx;
+                    }
+                    thrA = tA * 1.0001f + 0.01f;
+                    __syncwarp();
+                }
+            }
+            // box prefilter: lane tests quad (lane>>2) of each half against layer kk = lane&3
+            unsigned mask0, mask1;
+            {
+                float gx = fmaxf(fmaxf((l0x - bhi[0]) + sx, (blo[0] - h0x) - sx), 0.f);
+                float gy = fmaxf(fmaxf((l0y - bhi[1]) + sy, (blo[1] - h0y) - sy), 0.f);
+                float gz = fmaxf(fmaxf((l0z - bhi[2]) + sz, (blo[2] - h0z) - sz), 0.f);
+                mask0 = __ballot_sync(0xffffffffu, fmaf(gz, gz, fmaf(gx, gx, gy * gy)) < thrA);
+                gx = fmaxf(fmaxf((l1x - bhi[0]) + sx, (blo[0] - h1x) - sx), 0.f);
+                gy = fmaxf(fmaxf((l1y - bhi[1]) + sy, (blo[1] - h1y) - sy), 0.f);
+                gz = fmaxf(fmaxf((l1z - bhi[2]) + sz, (blo[2] - h1z) - sz), 0.f);
+                mask1 = __ballot_sync(0xffffffffu, fmaf(gz, gz, fmaf(gx, gx, gy * gy)) < thrA);
+            }
+            if (mask0 | mask1) {
+                const int nquads = (min(T4_JC, cend - coff) + 3) >> 2;
+                if (wrap)
+                    t4_chunk<MODE, true>(bx, by, bz, bt, nquads, mask0, mask1, npx, npy, npz, thr, fvb, wcst, sx, sy, sz,
+                                         c2u, pau, pbu, ax, ay, az, cnt);
+                else
+                    t4_chunk<MODE, false>(bx, by, bz, bt, nquads, mask0, mask1, npx, npy, npz, thr, fvb, wcst, sx, sy,
+                                          sz, c2u, pau, pbu, ax, ay, az, cnt);
+            }
+            buf ^= 1; // the other buffer was last read one chunk ago by this same warp
+        }
+#undef T4_ADVANCE
+
+        // ---- write back: the particle itself was tested too (d = 0, force term exactly 0) ----
+#pragma unroll
+        for (int k = 0; k < TK_IPT; k++) {
+            const int il = k * 32 + lane;
+            if (il < ni) {
+                float x0, x1, y0, y1, z0, z1;
+                tk_unpack(ax[k], x0, x1);
+                tk_unpack(ay[k], y0, y1);
+                tk_unpack(az[k], z0, z1);
+                const int ti = (int)((tis >> (4 * k)) & 15u);
+                const int self_ok = (MODE ? s_tab[(ti * T + ti) * 4 + 3] : cutu) > 0.f ? 1 : 0;
+                frc4[i_begin + il] = make_float4(x0 + x1, y0 + y1, z0 + z1, __int_as_float(cnt[k] - self_ok));
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// The type-homogeneous j copy (MODE 1): positions sorted by (xy row, type, z cell, Morton).
+// Built from the cell-sorted array by ONE stable sort on key = row * T + type (the cell-sorted
+// order already is (row, z cell, Morton)), a gather, and a lower-bound pass.
+// ---------------------------------------------------------------------------------------------
+__global__ void homog_key_kernel(const float4* __restrict__ pos4, const int* __restrict__ cell_start, int ncell,
+                                 int nz, int T, int nslots, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals,
+                                 int* __restrict__ cell_of) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nslots) return;
+    uint32_t key = (uint32_t)((ncell / nz) * T); // sentinel: slot holds no particle
+    int cell = -1;
+    if (k >= cell_start[0] && k < cell_start[ncell]) {
+        int lo = 0, hi = ncell; // last cell with cell_start[cell] <= k
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (cell_start[mid] <= k) lo = mid; else hi = mid;
+        }
+        cell = lo;
+        int t = (int)__float_as_uint(pos4[k].w);
+        t = t < 0 ? 0 : (t > T - 1 ? T - 1 : t);
+        key = (uint32_t)((cell / nz) * T + t);
+    }
+    keys[k] = key;
+    vals[k] = (uint32_t)k;
+    cell_of[k] = cell;
+}
+
+__global__ void homog_gather_kernel(const uint32_t* __restrict__ skeys, const uint32_t* __restrict__ svals,
+                                    const float4* __restrict__ pos4, const int* __restrict__ cell_of, int nz,
+                                    int nslots, float4* __restrict__ posj, uint32_t* __restrict__ comp) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nslots) return;
+    const uint32_t src = svals[k];
+    const int cell = cell_of[src];
+    posj[k] = pos4[src];
+    comp[k] = cell >= 0 ? skeys[k] * (uint32_t)nz + (uint32_t)(cell % nz) : 0xffffffffu;
+}
+
+// startj[e] = first index of the sorted copy whose composite key (row*T + type)*nz + cz is >= e
+__global__ void homog_bounds_kernel(const uint32_t* __restrict__ comp, int nslots, int* __restrict__ startj, int nkeys) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e > nkeys) return;
+    int lo = 0, hi = nslots;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (comp[mid] < (uint32_t)e) lo = mid + 1; else hi = mid;
+    }
+    startj[e] = lo;
+}

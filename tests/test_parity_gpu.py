@@ -67,7 +67,7 @@ CASES = [
 
 
 @pytest.mark.parametrize("name,n,mode,over,radio", CASES)
-@pytest.mark.parametrize("kernel", [1, 2])
+@pytest.mark.parametrize("kernel", [1, 2, 3])
 def test_step_parity(name, n, mode, over, radio, kernel):
     p, table, r0 = U.config(name, **over)
     radio = np.float32(radio) if radio is not None else r0
@@ -278,7 +278,7 @@ def test_newton_third_law_with_symmetric_matrix():
 
 
 @pytest.mark.parametrize("tag", ["settings", "eater_radii_wrap", "defaults", "pulser_edge"])
-@pytest.mark.parametrize("kernel", [1, 2])
+@pytest.mark.parametrize("kernel", [1, 2, 3])
 def test_against_reference_kernel_golden(tag, kernel):
     """The engine against the REFERENCE'S OWN kernel output (tests/golden, generated on a B200 by
     the unmodified reference .cu one warp at a time): neighbour counts bit-exact, forces 1e-5."""

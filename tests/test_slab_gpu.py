@@ -38,7 +38,7 @@ def by_id(sim, n):
     return out, cnt
 
 
-@pytest.mark.parametrize("kernel", [1, 2])
+@pytest.mark.parametrize("kernel", [1, 2, 3])
 @pytest.mark.parametrize("name,n,mode,over,radio", [
     ("settings", 20000, "uniform", {}, None),
     ("eater", 30000, "cube", {}, None),
