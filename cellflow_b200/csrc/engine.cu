@@ -968,8 +968,13 @@ static int launch_force(cf_sim* s) {
     // the tile kernels decide the minimum-image wrap per neighbour cell: >= 4 cells per periodic axis
     const bool wrap_ok = s->sc.dims[1] >= 4 && s->sc.dims[2] >= 4 && global_nx >= 4;
     const bool v3_ok = wrap_ok && (s->sc.uniform_radius || s->half_bound_ok);
-    bool tile_ok = wrap_ok && tile_kernel_applicable(s->sc, n, s->ncell);
-    if (kernel == 0) kernel = tile_ok ? 3 : 1;
+    const bool tile_ok = wrap_ok && tile_kernel_applicable(s->sc, n, s->ncell);
+    if (kernel == 0) {
+        // generation 4 streams one sub-run per (neighbour run, type) when the radii differ per type:
+        // it needs sub-runs long enough to fill its 64-particle chunks
+        const double subrun = 3.0 * (double)n / (double)std::max(s->ncell, 1) / (s->sc.uniform_radius ? 1.0 : (double)s->T);
+        kernel = !tile_ok ? 1 : (subrun >= 40.0 ? 3 : (v3_ok ? 2 : 1));
+    }
     if (kernel == 3 && !wrap_ok) kernel = 1;
     if (kernel == 2 && !v3_ok) kernel = 1;
     s->last_force_kernel = kernel;
@@ -989,15 +994,18 @@ static int launch_force(cf_sim* s) {
         LAUNCH(s, build_tiles_kernel, div_up(s->ncell, 256), 256, 0, s->cell_start, s->ncell, s->sc.x_off,
                s->sc.x_off + s->sc.x_cells - 1,
                s->sc.dims[1] * s->sc.dims[2], s->d_tiles, s->d_tile_ctrl);
-        int grid = s->sm_count * 4;
-        if (kernel == 3) {
+        if (kernel == 3) { // persistent grid: 5 CTAs of 4 independent warps per SM (96 registers per thread)
+            const int grid = s->sm_count * 5;
             if (homog)
                 LAUNCH(s, force_tile4_kernel<1>, grid, T4_WARPS * 32, 0, pos, s->cell_start, s->h_pos, s->h_start,
                        s->d_tiles, s->d_tile_ctrl, s->frc, s->sc, s->d_tables);
             else
                 LAUNCH(s, force_tile4_kernel<0>, grid, T4_WARPS * 32, 0, pos, s->cell_start, pos, s->cell_start,
                        s->d_tiles, s->d_tile_ctrl, s->frc, s->sc, s->d_tables);
-        } else if (s->sc.uniform_radius)
+            return 0;
+        }
+        const int grid = s->sm_count * 4;
+        if (s->sc.uniform_radius)
             LAUNCH(s, force_tile_kernel<true>, grid, TK_THREADS, 0, pos, s->cell_start, s->d_tiles, s->d_tile_ctrl,
                    s->frc, s->sc, s->d_tables, 0.f, s->d_half);
         else
@@ -1387,6 +1395,8 @@ extern "C" int cf_get_stats(cf_sim* s, cf_stats* st) {
     st->stencil = 1;
     st->n_owned = s->n;
     st->n_ghost = 0;
+    st->force_kernel = s->last_force_kernel;
+    st->reserved = 0;
     if (s->slab) {
         int g[2] = {0, 0};
         CU(cudaMemcpy(g, s->d_slab_counts + 4, 2 * sizeof(int), cudaMemcpyDeviceToHost));

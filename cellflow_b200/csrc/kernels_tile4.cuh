@@ -20,8 +20,10 @@
 //   * LEANER FORCE PATH.  Accept bits as integer masks (set.lt.s32.f32): the neighbour count is
 //     two IADD3, the rejected pairs are zeroed with one AND on the bits of s (so a NaN/Inf of a
 //     padded or rejected pair can never leak); no generic-pointer arithmetic on shared memory.
-//   * one code path for every tile occupancy (empty layers have empty boxes and are never live)
-//     and prefetch across run boundaries.
+//   * 96 REGISTERS, 5 CTAs per SM: scalar force accumulators, layer boxes in shared memory, the
+//     next chunk prefetched into L1 by a hint instead of into registers (and across run
+//     boundaries); one code path for every tile occupancy (empty layers have empty boxes and
+//     are never live).
 //
 // Exactness is unchanged: displacement = (jx + (-px)) [+ s], s in {-W, 0, +W} per run (exact,
 // see kernels_tile.cuh), d2 = fma(dz,dz, fma(dx,dx, dy*dy)), accept <=> d2 < cut2[ti][tj].
@@ -41,7 +43,8 @@ struct T4Shared {
     float z[T4_WARPS][2][T4_JC];
     int t[T4_WARPS][2][T4_JC];                       // MODE 0: byte offset of j's row in s_fv
     int2 sub[T4_WARPS][MODE ? T4_MAXSUB : TK_MAX_RUNS]; // [j0, j1) of every (sub-)run
-    float4 cst[MODE ? T4_WARPS : 1][4][32];          // MODE 1: (c2, A, B, -) of (layer, lane) for the current sub-run
+    float4 cst[MODE ? T4_WARPS : 1][4][32];          // MODE 1: (c2, A, B, cut2) of (layer, lane) for the current sub-run
+    float4 box[T4_WARPS][4][2];                      // (lo.xyz, prefilter threshold), (hi.xyz, -) of every layer
 };
 
 __device__ __forceinline__ int t4_setlt(float a, float b) { // 0xffffffff if a < b else 0
@@ -73,10 +76,32 @@ __device__ __forceinline__ float t4_lds(unsigned addr) {
 // MODE 0: c2, nb = -att/Reff are kernel constants, fv comes from the transposed table in shared
 // memory; MODE 1: c2, A = fv * rep, B = -fv * att / Reff are per (lane, layer) constants of the
 // current sub-run.  Rejected pairs: the bits of s are ANDed with the accept mask.
+// Force accumulators of one (lane, layer): scalar (3 registers); the packed products of a block are
+// folded in with 12 FFMA (same FMA-pipe cycles as 6 packed FFMA2 into 6 registers).
+struct T4AccScalar {
+    float x, y, z;
+    __device__ __forceinline__ void zero() { x = y = z = 0.f; }
+    __device__ __forceinline__ void add(u64 sa, u64 sb, u64 dxa, u64 dya, u64 dza, u64 dxb, u64 dyb, u64 dzb) {
+        float s0, s1, s2, s3, a0, a1, b0, b1;
+        tk_unpack(sa, s0, s1);
+        tk_unpack(sb, s2, s3);
+        tk_unpack(dxa, a0, a1);
+        tk_unpack(dxb, b0, b1);
+        x = fmaf(s3, b1, fmaf(s2, b0, fmaf(s1, a1, fmaf(s0, a0, x))));
+        tk_unpack(dya, a0, a1);
+        tk_unpack(dyb, b0, b1);
+        y = fmaf(s3, b1, fmaf(s2, b0, fmaf(s1, a1, fmaf(s0, a0, y))));
+        tk_unpack(dza, a0, a1);
+        tk_unpack(dzb, b0, b1);
+        z = fmaf(s3, b1, fmaf(s2, b0, fmaf(s1, a1, fmaf(s0, a0, z))));
+    }
+    __device__ __forceinline__ float3 sum() const { return make_float3(x, y, z); }
+};
+
 template <int MODE>
 __device__ __forceinline__ void t4_live(u64 dxa, u64 dya, u64 dza, u64 d2a, u64 dxb, u64 dyb, u64 dzb, u64 d2b,
                                         float a0, float a1, float b0, float b1, float thr, float c2, float pa,
-                                        float pb, unsigned fv_base, int4 Tq, u64& ax, u64& ay, u64& az, int& cnt) {
+                                        float pb, unsigned fv_base, int4 Tq, T4AccScalar& acc, int& cnt) {
     const int m0 = t4_setlt(a0, thr), m1 = t4_setlt(a1, thr), m2 = t4_setlt(b0, thr), m3 = t4_setlt(b1, thr);
     const u64 eps = tk_pack(0.0001f, 0.0001f);
     const u64 xa = tk_add2(d2a, eps), xb = tk_add2(d2b, eps);
@@ -102,37 +127,44 @@ __device__ __forceinline__ void t4_live(u64 dxa, u64 dya, u64 dza, u64 d2a, u64 
     sa = tk_pack(t4_and(s0, m0), t4_and(s1, m1));
     sb = tk_pack(t4_and(s2, m2), t4_and(s3, m3));
     cnt -= (m0 + m1) + (m2 + m3);
-    ax = tk_fma2(sb, dxb, tk_fma2(sa, dxa, ax));
-    ay = tk_fma2(sb, dyb, tk_fma2(sa, dya, ay));
-    az = tk_fma2(sb, dzb, tk_fma2(sa, dza, az));
+    acc.add(sa, sb, dxa, dya, dza, dxb, dyb, dzb);
 }
 
-// All live (layer, quad) blocks of one staged chunk.
+// All live (layer, quad) blocks of one staged chunk.  MODE 0 takes the uniform threshold and derives
+// the table address from the packed types; MODE 1 reads (c2, A, B, cut2) of (layer, lane) from
+// shared memory per block.
 template <int MODE, bool WRAP>
-__device__ __forceinline__ void t4_chunk(const float* __restrict__ xs, const float* __restrict__ ys,
-                                         const float* __restrict__ zs, const int* __restrict__ ts, int nquads,
-                                         unsigned mask0, unsigned mask1, const float (&npx)[TK_IPT],
-                                         const float (&npy)[TK_IPT], const float (&npz)[TK_IPT],
-                                         const float (&thr)[TK_IPT], const unsigned (&fvb)[TK_IPT],
-                                         const float4* __restrict__ cst, float sx, float sy, float sz, float c2u,
-                                         float pau, float pbu, u64 (&ax)[TK_IPT], u64 (&ay)[TK_IPT],
-                                         u64 (&az)[TK_IPT], int (&cnt)[TK_IPT]) {
+__device__ __forceinline__ void t4_chunk(unsigned sbase, int nquads, unsigned mask0, unsigned mask1,
+                                         const float (&npx)[TK_IPT], const float (&npy)[TK_IPT],
+                                         const float (&npz)[TK_IPT], unsigned tis4, unsigned s_tab_addr,
+                                         const float4* __restrict__ cst, float sx, float sy, float sz, float cutu,
+                                         float c2u, float pau, float pbu, T4AccScalar (&acc)[TK_IPT],
+                                         int (&cnt)[TK_IPT]) {
     const u64 sx2 = tk_pack(sx, sx), sy2 = tk_pack(sy, sy), sz2 = tk_pack(sz, sz);
+    constexpr unsigned STRIDE = T4_WARPS * 2 * T4_JC * 4; // bytes between the x, y, z, t arrays
+    // bit 4*q + k of the 64-bit mask = (quad q, layer k) passed the box prefilter
+    unsigned long long m = ((unsigned long long)mask1 << 32) | mask0;
+    if (nquads < 16) m &= (1ull << (4 * nquads)) - 1ull;
+    unsigned qa = sbase;
 #pragma unroll 1
-    for (int q = 0; q < nquads; q++) {
-        const unsigned m4 = (((q & 8) ? mask1 : mask0) >> ((q & 7) << 2)) & 15u;
+    for (; m != 0ull; m >>= 4, qa += 16u) {
+        const unsigned m4 = (unsigned)m & 15u;
         if (m4 == 0u) continue; // no layer's box comes near this quad's box
-        const float4 X = *reinterpret_cast<const float4*>(xs + 4 * q);
-        const float4 Y = *reinterpret_cast<const float4*>(ys + 4 * q);
-        const float4 Z = *reinterpret_cast<const float4*>(zs + 4 * q);
+        float4 X, Y, Z;
         int4 Tq = make_int4(0, 0, 0, 0);
-        if (MODE == 0) Tq = *reinterpret_cast<const int4*>(ts + 4 * q);
+        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(X.x), "=f"(X.y), "=f"(X.z), "=f"(X.w) : "r"(qa));
+        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(Y.x), "=f"(Y.y), "=f"(Y.z), "=f"(Y.w) : "r"(qa + STRIDE));
+        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(Z.x), "=f"(Z.y), "=f"(Z.z), "=f"(Z.w) : "r"(qa + 2 * STRIDE));
+        if (MODE == 0)
+            asm volatile("ld.shared.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(Tq.x), "=r"(Tq.y), "=r"(Tq.z), "=r"(Tq.w) : "r"(qa + 3 * STRIDE));
         const u64 xa = tk_pack(X.x, X.y), xb = tk_pack(X.z, X.w);
         const u64 ya = tk_pack(Y.x, Y.y), yb = tk_pack(Y.z, Y.w);
         const u64 za = tk_pack(Z.x, Z.y), zb = tk_pack(Z.z, Z.w);
 #pragma unroll
         for (int k = 0; k < TK_IPT; k++) {
             if (!(m4 & (1u << k))) continue; // warp-uniform
+            float4 cs = make_float4(c2u, pau, pbu, cutu);
+            if (MODE == 1) cs = cst[k * 32];
             const u64 px = tk_pack(npx[k], npx[k]), py = tk_pack(npy[k], npy[k]), pz = tk_pack(npz[k], npz[k]);
             u64 dxa = tk_add2(xa, px), dxb = tk_add2(xb, px);
             u64 dya = tk_add2(ya, py), dyb = tk_add2(yb, py);
@@ -148,21 +180,17 @@ __device__ __forceinline__ void t4_chunk(const float* __restrict__ xs, const flo
             tk_unpack(d2a, a0, a1);
             tk_unpack(d2b, b0, b1);
             const float mn = fminf(fminf(a0, a1), fminf(b0, b1));
-            if (__any_sync(0xffffffffu, mn < thr[k])) {
-                float c2 = c2u, pa = pau, pb = pbu;
-                if (MODE == 1) {
-                    const float4 cs = cst[k * 32];
-                    c2 = cs.x, pa = cs.y, pb = cs.z;
-                }
-                t4_live<MODE>(dxa, dya, dza, d2a, dxb, dyb, dzb, d2b, a0, a1, b0, b1, thr[k], c2, pa, pb, fvb[k], Tq,
-                              ax[k], ay[k], az[k], cnt[k]);
+            if (__any_sync(0xffffffffu, mn < cs.w)) {
+                const unsigned fva = s_tab_addr + ((tis4 >> (8 * k)) & 255u);
+                t4_live<MODE>(dxa, dya, dza, d2a, dxb, dyb, dzb, d2b, a0, a1, b0, b1, cs.w, cs.x, cs.y, cs.z, fva, Tq,
+                              acc[k], cnt[k]);
             }
         }
     }
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(T4_WARPS * 32, 4)
+__global__ void __launch_bounds__(T4_WARPS * 32, 5)
 force_tile4_kernel(const float4* __restrict__ pos4, const int* __restrict__ cell_start,
                    const float4* __restrict__ posj, const int* __restrict__ startj,
                    const int2* __restrict__ tiles, int* __restrict__ ctrl, float4* __restrict__ frc4, StepConst c,
@@ -191,13 +219,11 @@ force_tile4_kernel(const float4* __restrict__ pos4, const int* __restrict__ cell
     const float cutu = c.cut2_uniform;
     const float c2u = c.nk_log2e * c.inv_reff_uniform * c.inv_reff_uniform;
     const float pau = c.repulsion, pbu = -(c.attraction * c.inv_reff_uniform);
-    float* const wx = &sm.x[warp][0][0];
-    float* const wy = &sm.y[warp][0][0];
-    float* const wz = &sm.z[warp][0][0];
-    int* const wt = &sm.t[warp][0][0];
     int2* const wsub = &sm.sub[warp][0];
     float4* const wcst = &sm.cst[MODE ? warp : 0][0][lane];
     const unsigned s_tab_addr = (unsigned)__cvta_generic_to_shared(s_tab);
+    const unsigned stage_addr = (unsigned)__cvta_generic_to_shared(&sm.x[warp][0][0]); // + buf*256 + 4*slot
+    constexpr unsigned STRIDE = T4_WARPS * 2 * T4_JC * 4;
     const int kk = lane & 3; // the layer this lane tests in the box prefilter
 
     for (;;) {
@@ -212,38 +238,35 @@ force_tile4_kernel(const float4* __restrict__ pos4, const int* __restrict__ cell
         const int ni = min(cell_start[cell + 1] - i_begin, TK_TI);
 
         // ---- neighbour runs: lane r < 18 holds run r = (row r/2 of the 3x3 (x,y) rows, z segment r%2)
-        float r_sx = 0.f, r_sy = 0.f, r_sz = 0.f; // minimum-image shift of the run: -W, 0 or +W per axis
+        int r_code = 0; // minimum-image shift of the run, 2 bits per axis: 1 = -W, 2 = +W
         int r_row = -1, r_z0 = 0, r_z1 = 0;
         if (lane < TK_MAX_RUNS) {
             int rho = lane >> 1, seg = lane & 1;
             int x = cx + rho / 3 - 1, y = cy + rho % 3 - 1;
             bool valid = true;
             if (c.periodic_x) {
-                if (x < 0) { x = c.dims[0] - 1; r_sx = -c.W[0]; } else if (x >= c.dims[0]) { x = 0; r_sx = c.W[0]; }
+                if (x < 0) { x = c.dims[0] - 1; r_code |= 1; } else if (x >= c.dims[0]) { x = 0; r_code |= 2; }
             } else { // slab mode: i-cells are layers 1..dims-2, so x stays inside [0, dims-1]
                 if (x < 0 || x >= c.dims[0]) valid = false;
-                else if (x == 0) r_sx = c.gshift_lo;
-                else if (x == c.dims[0] - 1) r_sx = c.gshift_hi;
+                else if (x == 0) r_code |= (c.gshift_lo < 0.f ? 1 : (c.gshift_lo > 0.f ? 2 : 0));
+                else if (x == c.dims[0] - 1) r_code |= (c.gshift_hi < 0.f ? 1 : (c.gshift_hi > 0.f ? 2 : 0));
             }
-            if (y < 0) { y = ny - 1; r_sy = -c.W[1]; } else if (y >= ny) { y = 0; r_sy = c.W[1]; }
+            if (y < 0) { y = ny - 1; r_code |= 4; } else if (y >= ny) { y = 0; r_code |= 8; }
             if (seg == 0) {
                 r_z0 = max(cz - 1, 0);
                 r_z1 = min(cz + 1, nz - 1);
             } else if (cz == 0) {
                 r_z0 = r_z1 = nz - 1;
-                r_sz = -c.W[2];
+                r_code |= 16;
             } else if (cz == nz - 1) {
                 r_z0 = r_z1 = 0;
-                r_sz = c.W[2];
+                r_code |= 32;
             } else {
                 valid = false;
             }
             if (valid) r_row = x * ny + y;
         }
         // (sub-)run list in shared memory: MODE 0 entry r = run r; MODE 1 entry r*T + t = type t of run r
-        // 2 bits per axis: 1 = -W, 2 = +W
-        const int r_code = (r_sx < 0.f ? 1 : (r_sx > 0.f ? 2 : 0)) | (r_sy < 0.f ? 4 : (r_sy > 0.f ? 8 : 0)) |
-                           (r_sz < 0.f ? 16 : (r_sz > 0.f ? 32 : 0));
         __syncwarp();
         const int nsub = MODE ? TK_MAX_RUNS * T : TK_MAX_RUNS;
         for (int e0 = 0; e0 < nsub; e0 += 32) {
@@ -261,17 +284,12 @@ force_tile4_kernel(const float4* __restrict__ pos4, const int* __restrict__ cell
                 wsub[e] = jj;
             }
         }
-        __syncwarp();
 
         // ---- my i particles: layer k holds slots i_begin + 32k + lane ----
-        float npx[TK_IPT], npy[TK_IPT], npz[TK_IPT], thr[TK_IPT];
-        unsigned fvb[TK_IPT]; // MODE 0: shared address of s_tab[ti] (MODE 1: unused)
-        unsigned tis = 0;     // the 4 types of this lane's particles, 4 bits each
-        u64 ax[TK_IPT], ay[TK_IPT], az[TK_IPT];
+        float npx[TK_IPT], npy[TK_IPT], npz[TK_IPT];
+        unsigned tis4 = 0; // byte k = 4 * type of this lane's particle in layer k
+        T4AccScalar acc[TK_IPT];
         int cnt[TK_IPT];
-        float blo[3], bhi[3]; // bounding box of layer kk
-        blo[0] = blo[1] = blo[2] = T4_INF;
-        bhi[0] = bhi[1] = bhi[2] = -T4_INF;
 #pragma unroll
         for (int k = 0; k < TK_IPT; k++) {
             const int il = k * 32 + lane;
@@ -279,20 +297,22 @@ force_tile4_kernel(const float4* __restrict__ pos4, const int* __restrict__ cell
             const float4 p = v ? pos4[i_begin + il] : make_float4(-TK_FAR, -TK_FAR, -TK_FAR, 0.f);
             const int ti = v ? (int)__float_as_uint(p.w) : 0;
             npx[k] = -p.x, npy[k] = -p.y, npz[k] = -p.z;
-            fvb[k] = MODE ? 0u : s_tab_addr + (unsigned)(ti * 4);
-            tis |= (unsigned)ti << (4 * k);
-            thr[k] = MODE ? 0.f : (v ? cutu : 0.f);
-            ax[k] = ay[k] = az[k] = tk_pack(0.f, 0.f);
+            tis4 |= (unsigned)(ti * 4) << (8 * k);
+            acc[k].zero();
             cnt[k] = 0;
             const float lx = t4_warp_min(v ? p.x : T4_INF), hx = t4_warp_max(v ? p.x : -T4_INF);
             const float ly = t4_warp_min(v ? p.y : T4_INF), hy = t4_warp_max(v ? p.y : -T4_INF);
             const float lz = t4_warp_min(v ? p.z : T4_INF), hz = t4_warp_max(v ? p.z : -T4_INF);
-            if (kk == k) blo[0] = lx, blo[1] = ly, blo[2] = lz, bhi[0] = hx, bhi[1] = hy, bhi[2] = hz;
+            if (lane == 0) { // bounding box of the layer + prefilter threshold (squared box gap)
+                sm.box[warp][k][0] = make_float4(lx, ly, lz, cutu * 1.0001f + 0.01f);
+                sm.box[warp][k][1] = make_float4(hx, hy, hz, 0.f);
+            }
         }
-        float thrA = MODE ? 0.f : cutu * 1.0001f + 0.01f; // prefilter threshold of layer kk (squared box gap)
+        __syncwarp();
 
-        // ---- stream the chunks of all (sub-)runs, prefetching across run boundaries ----
-        int si = -1, off = 0, end = 0; // prefetch cursor
+        // ---- stream the chunks of all (sub-)runs; the next chunk is prefetched across run boundaries
+        //      into L1 by a prefetch hint, which holds no registers ----
+        int si = -1, off = 0, end = 0; // cursor
         bool have;
 #define T4_ADVANCE()                                \
     do {                                            \
@@ -313,16 +333,20 @@ force_tile4_kernel(const float4* __restrict__ pos4, const int* __restrict__ cell
         bool wrap = false;
         while (have) {
             const int csi = si, coff = off, cend = end;
-            // publish the prefetched chunk
-            float* bx = wx + buf * T4_JC;
-            float* by = wy + buf * T4_JC;
-            float* bz = wz + buf * T4_JC;
-            int* bt = wt + buf * T4_JC;
-            bx[lane] = q0.x, by[lane] = q0.y, bz[lane] = q0.z;
-            bx[lane + 32] = q1.x, by[lane + 32] = q1.y, bz[lane + 32] = q1.z;
-            if (MODE == 0) {
-                bt[lane] = (int)__float_as_uint(q0.w) * (T * 4);
-                bt[lane + 32] = (int)__float_as_uint(q1.w) * (T * 4);
+            // publish the chunk
+            const unsigned sbase = stage_addr + (unsigned)buf * (T4_JC * 4);
+            {
+                const unsigned a = sbase + 4u * (unsigned)lane;
+                asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(q0.x));
+                asm volatile("st.shared.f32 [%0], %1;" ::"r"(a + STRIDE), "f"(q0.y));
+                asm volatile("st.shared.f32 [%0], %1;" ::"r"(a + 2 * STRIDE), "f"(q0.z));
+                asm volatile("st.shared.f32 [%0], %1;" ::"r"(a + 128u), "f"(q1.x));
+                asm volatile("st.shared.f32 [%0], %1;" ::"r"(a + 128u + STRIDE), "f"(q1.y));
+                asm volatile("st.shared.f32 [%0], %1;" ::"r"(a + 128u + 2 * STRIDE), "f"(q1.z));
+                if (MODE == 0) {
+                    asm volatile("st.shared.s32 [%0], %1;" ::"r"(a + 3 * STRIDE), "r"((int)__float_as_uint(q0.w) * (T * 4)));
+                    asm volatile("st.shared.s32 [%0], %1;" ::"r"(a + 128u + 3 * STRIDE), "r"((int)__float_as_uint(q1.w) * (T * 4)));
+                }
             }
             // bounding boxes of the quads: 4 consecutive lanes hold one quad of each half
             const bool v0 = coff + lane < cend, v1 = coff + 32 + lane < cend;
@@ -346,12 +370,12 @@ force_tile4_kernel(const float4* __restrict__ pos4, const int* __restrict__ cell
                 h1z = fmaxf(h1z, __shfl_xor_sync(0xffffffffu, h1z, o));
             }
             __syncwarp();
-            // prefetch the next chunk (possibly of the next run) while this one is processed
+            // the next chunk (possibly of the next run)
             T4_ADVANCE();
-            q0 = make_float4(TK_FAR, TK_FAR, TK_FAR, 0.f);
-            q1 = q0;
-            if (have && off + lane < end) q0 = posj[off + lane];
-            if (have && off + 32 + lane < end) q1 = posj[off + 32 + lane];
+            if (have && lane < 9) { // 64 float4 = 1 KiB: at most 9 lines of 128 B
+                const float4* pf = posj + min(off + 8 * lane, end - 1);
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(pf));
+            }
 
             if (csi != cur_si) { // a new (sub-)run: its minimum-image shift, MODE 1: its pair constants
                 cur_si = csi;
@@ -364,42 +388,48 @@ force_tile4_kernel(const float4* __restrict__ pos4, const int* __restrict__ cell
                 if (MODE == 1) {
                     const int tj = csi - r * T;
                     const char* row = reinterpret_cast<const char*>(s_tab) + tj * (T * 16);
-                    float tA = 0.f;
 #pragma unroll
                     for (int k = 0; k < TK_IPT; k++) {
-                        const float4 e = *reinterpret_cast<const float4*>(row + ((tis >> (4 * k)) & 15u) * 16u);
-                        const bool v = k * 32 + lane < ni;
-                        thr[k] = v ? e.w : 0.f;
-                        wcst[k * 32] = make_float4(e.x, e.y, e.z, 0.f);
-                        const float mx = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(thr[k]))); // thr >= 0
-                        if (kk == k) tA = mx;
+                        float4 e = *reinterpret_cast<const float4*>(row + ((tis4 >> (8 * k)) & 255u) * 4u);
+                        if (!(k * 32 + lane < ni)) e.w = 0.f; // no particle: never accepts
+                        wcst[k * 32] = e;
+                        const float mx = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(e.w))); // cut2 >= 0
+                        if (lane == 0) sm.box[warp][k][0].w = mx * 1.0001f + 0.01f;
                     }
-                    thrA = tA * 1.0001f + 0.01f;
                     __syncwarp();
                 }
             }
             // box prefilter: lane tests quad (lane>>2) of each half against layer kk = lane&3
             unsigned mask0, mask1;
             {
+                const float4 b0 = sm.box[warp][kk][0], b1 = sm.box[warp][kk][1];
+                const float blo[3] = {b0.x, b0.y, b0.z}, bhi[3] = {b1.x, b1.y, b1.z};
+                const float tA = b0.w;
                 float gx = fmaxf(fmaxf((l0x - bhi[0]) + sx, (blo[0] - h0x) - sx), 0.f);
                 float gy = fmaxf(fmaxf((l0y - bhi[1]) + sy, (blo[1] - h0y) - sy), 0.f);
                 float gz = fmaxf(fmaxf((l0z - bhi[2]) + sz, (blo[2] - h0z) - sz), 0.f);
-                mask0 = __ballot_sync(0xffffffffu, fmaf(gz, gz, fmaf(gx, gx, gy * gy)) < thrA);
+                mask0 = __ballot_sync(0xffffffffu, fmaf(gz, gz, fmaf(gx, gx, gy * gy)) < tA);
                 gx = fmaxf(fmaxf((l1x - bhi[0]) + sx, (blo[0] - h1x) - sx), 0.f);
                 gy = fmaxf(fmaxf((l1y - bhi[1]) + sy, (blo[1] - h1y) - sy), 0.f);
                 gz = fmaxf(fmaxf((l1z - bhi[2]) + sz, (blo[2] - h1z) - sz), 0.f);
-                mask1 = __ballot_sync(0xffffffffu, fmaf(gz, gz, fmaf(gx, gx, gy * gy)) < thrA);
+                mask1 = __ballot_sync(0xffffffffu, fmaf(gz, gz, fmaf(gx, gx, gy * gy)) < tA);
             }
             if (mask0 | mask1) {
                 const int nquads = (min(T4_JC, cend - coff) + 3) >> 2;
                 if (wrap)
-                    t4_chunk<MODE, true>(bx, by, bz, bt, nquads, mask0, mask1, npx, npy, npz, thr, fvb, wcst, sx, sy, sz,
-                                         c2u, pau, pbu, ax, ay, az, cnt);
+                    t4_chunk<MODE, true>(sbase, nquads, mask0, mask1, npx, npy, npz, tis4, s_tab_addr, wcst, sx, sy, sz,
+                                         cutu, c2u, pau, pbu, acc, cnt);
                 else
-                    t4_chunk<MODE, false>(bx, by, bz, bt, nquads, mask0, mask1, npx, npy, npz, thr, fvb, wcst, sx, sy,
-                                          sz, c2u, pau, pbu, ax, ay, az, cnt);
+                    t4_chunk<MODE, false>(sbase, nquads, mask0, mask1, npx, npy, npz, tis4, s_tab_addr, wcst, sx, sy, sz,
+                                          cutu, c2u, pau, pbu, acc, cnt);
             }
             buf ^= 1; // the other buffer was last read one chunk ago by this same warp
+            if (have) { // the next chunk: an L1 hit after the prefetch hint
+                q0 = make_float4(TK_FAR, TK_FAR, TK_FAR, 0.f);
+                q1 = q0;
+                if (off + lane < end) q0 = posj[off + lane];
+                if (off + 32 + lane < end) q1 = posj[off + 32 + lane];
+            }
         }
 #undef T4_ADVANCE
 
@@ -408,13 +438,10 @@ force_tile4_kernel(const float4* __restrict__ pos4, const int* __restrict__ cell
         for (int k = 0; k < TK_IPT; k++) {
             const int il = k * 32 + lane;
             if (il < ni) {
-                float x0, x1, y0, y1, z0, z1;
-                tk_unpack(ax[k], x0, x1);
-                tk_unpack(ay[k], y0, y1);
-                tk_unpack(az[k], z0, z1);
-                const int ti = (int)((tis >> (4 * k)) & 15u);
+                const float3 f = acc[k].sum();
+                const int ti = (int)((tis4 >> (8 * k)) & 255u) >> 2;
                 const int self_ok = (MODE ? s_tab[(ti * T + ti) * 4 + 3] : cutu) > 0.f ? 1 : 0;
-                frc4[i_begin + il] = make_float4(x0 + x1, y0 + y1, z0 + z1, __int_as_float(cnt[k] - self_ok));
+                frc4[i_begin + il] = make_float4(f.x, f.y, f.z, __int_as_float(cnt[k] - self_ok));
             }
         }
     }

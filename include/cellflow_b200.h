@@ -125,6 +125,8 @@ typedef struct cf_stats {
     int32_t grid[3];       /* cells per axis of the current cell grid */
     int32_t stencil;       /* half-width m of the (2m+1)^3 neighbour stencil */
     int32_t n_owned, n_ghost;
+    int32_t force_kernel;  /* pair-force kernel of the last step: 1 per-particle, 2 tile gen. 3, 3 tile gen. 4 */
+    int32_t reserved;
 } cf_stats;
 
 typedef struct cf_sim cf_sim;
