@@ -1255,7 +1255,8 @@ extern "C" int cf_build_graph(cf_sim* s, float dist, int max_conn, int* n_edges)
         if (int rc = radix_sort_pairs(s, s->gk, s->gv, count, (long long)nkeys + 1, &src)) return rc;
         LAUNCH(s, graph_gather_kernel, div_up(count, 256), 256, 0, s->gv[src], s->pos[s->cur], s->id[s->cur], count, s->gpos);
         LAUNCH(s, graph_bounds_kernel, div_up(nkeys + 1, 256), 256, 0, s->gk[src], count, s->gstart, nkeys);
-        LAUNCH(s, graph_kernel, div_up(count, CF_GRAPH_THREADS), CF_GRAPH_THREADS, 0, s->gpos, s->gv[src], s->gk[src], s->gstart, count, s->base,
+        LAUNCH(s, graph_kernel, div_up(count, CF_GRAPH_THREADS), CF_GRAPH_THREADS,
+               (size_t)3 * 2 * mc * CF_GRAPH_THREADS * sizeof(int), s->gpos, s->gv[src], s->gk[src], s->gstart, count, s->base,
                s->n, g, dist * dist, mc, s->edges, s->edge_slots, s->edge_cap, s->d_edge_count);
     }
     if (s->opt_timing) {

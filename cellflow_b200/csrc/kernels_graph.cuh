@@ -76,7 +76,12 @@ __global__ void graph_bounds_kernel(const uint32_t* __restrict__ skeys, int n, i
 // The per-thread candidate lists live in shared memory, laid out [entry][thread]: dynamic
 // indexing costs one conflict-free LDS/STS instead of a scattered local-memory transaction
 // per lane (the first version kept them in local memory and spent most of its time there).
+// The lists are sized for the actual 2*maxConn (dynamic shared memory: 7.5 KB per CTA at the
+// default maxConn = 5, so 32 CTAs = all 64 warps of an SM are resident), and the candidate loop
+// keeps CF_GRAPH_BATCH independent 16-byte loads in flight: the kernel is bound by the latency
+// of those (L2-resident) loads, not by arithmetic.
 #define CF_GRAPH_THREADS 64
+#define CF_GRAPH_BATCH 4
 struct GraphList {
     int* id;
     int* q;
@@ -91,13 +96,12 @@ graph_kernel(const float4* __restrict__ gpos, const uint32_t* __restrict__ gvals
              const int* __restrict__ gstart, int nq, int own_first, int n_own, GraphGrid g, float dist2,
              int max_conn, int2* __restrict__ edges, int2* __restrict__ edge_slots, int capacity,
              int* __restrict__ edge_count) {
-    __shared__ int s_id[CF_GRAPH_K * CF_GRAPH_THREADS];
-    __shared__ int s_q[CF_GRAPH_K * CF_GRAPH_THREADS];
-    __shared__ float s_d2[CF_GRAPH_K * CF_GRAPH_THREADS];
-    GraphList L{s_id + threadIdx.x, s_q + threadIdx.x, s_d2 + threadIdx.x};
+    extern __shared__ int s_lists[]; // [3][K][CF_GRAPH_THREADS]: id, graph position, d2
+    const int K = 2 * max_conn;
+    GraphList L{s_lists + threadIdx.x, s_lists + K * CF_GRAPH_THREADS + threadIdx.x,
+                reinterpret_cast<float*>(s_lists + 2 * K * CF_GRAPH_THREADS) + threadIdx.x};
     int q = blockIdx.x * blockDim.x + threadIdx.x;
     int ncand = 0, my_id = 0, my_slot = 0;
-    const int K = 2 * max_conn;
     bool active = false;
     if (q < nq) {
         uint32_t key = gkeys[q];
@@ -118,26 +122,34 @@ graph_kernel(const float4* __restrict__ gpos, const uint32_t* __restrict__ gvals
                     int row = tbase + (x * g.dims[1] + y) * g.dims[2];
                     // z-adjacent cells of one type are contiguous: one range per (x, y)
                     int j0 = gstart[row + z0], j1 = gstart[row + z1 + 1];
-                    for (int j = j0; j < j1; j++) {
-                        float4 o = gpos[j];
-                        int jid = __float_as_int(o.w);
-                        if (jid <= my_id) continue;
-                        float dx = __fsub_rn(o.x, p.x), dy = __fsub_rn(o.y, p.y), dz = __fsub_rn(o.z, p.z);
-                        float d2 = cf_dist2(dx, dy, dz);
-                        if (!(d2 < dist2)) continue;
-                        if (ncand == K && jid > L.I(K - 1)) continue;
-                        // insert into the id-sorted candidate list (drop the largest id when full)
-                        int pos = ncand < K ? ncand : K - 1;
-                        while (pos > 0 && L.I(pos - 1) > jid) {
-                            L.I(pos) = L.I(pos - 1);
-                            L.Q(pos) = L.Q(pos - 1);
-                            L.D(pos) = L.D(pos - 1);
-                            pos--;
+                    for (int jb = j0; jb < j1; jb += CF_GRAPH_BATCH) {
+                        float4 ob[CF_GRAPH_BATCH];
+#pragma unroll
+                        for (int u = 0; u < CF_GRAPH_BATCH; u++) // independent loads; id -1 is never a candidate
+                            ob[u] = jb + u < j1 ? gpos[jb + u] : make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+#pragma unroll
+                        for (int u = 0; u < CF_GRAPH_BATCH; u++) { // in index order, as the rule scans
+                            const float4 o = ob[u];
+                            const int j = jb + u;
+                            int jid = __float_as_int(o.w);
+                            if (jid <= my_id) continue;
+                            float dx = __fsub_rn(o.x, p.x), dy = __fsub_rn(o.y, p.y), dz = __fsub_rn(o.z, p.z);
+                            float d2 = cf_dist2(dx, dy, dz);
+                            if (!(d2 < dist2)) continue;
+                            if (ncand == K && jid > L.I(K - 1)) continue;
+                            // insert into the id-sorted candidate list (drop the largest id when full)
+                            int pos = ncand < K ? ncand : K - 1;
+                            while (pos > 0 && L.I(pos - 1) > jid) {
+                                L.I(pos) = L.I(pos - 1);
+                                L.Q(pos) = L.Q(pos - 1);
+                                L.D(pos) = L.D(pos - 1);
+                                pos--;
+                            }
+                            L.I(pos) = jid;
+                            L.Q(pos) = j;
+                            L.D(pos) = d2;
+                            if (ncand < K) ncand++;
                         }
-                        L.I(pos) = jid;
-                        L.Q(pos) = j;
-                        L.D(pos) = d2;
-                        if (ncand < K) ncand++;
                     }
                 }
             // stable insertion sort by d2 (.cu:235-243); the list is in index order, as the
