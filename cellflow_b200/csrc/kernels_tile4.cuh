@@ -2,16 +2,16 @@
 //
 // Same decomposition as kernels_tile.cuh (one WARP owns a tile of <= 128 particles of one cell as
 // 4 register-resident layers of 32; the 27 neighbour cells are streamed as <= 18 contiguous runs
-// through a warp-private double buffer, 64 j per chunk; one warp vote per (layer, quad of 4 j)
+// through a warp-private double buffer, 128 j per chunk; one warp vote per (layer, quad of 4 j)
 // gates the force terms), with what the round-1 ncu captures asked for
 // (profiles/r01_force_kernel_history.md, profiles/r02_force_kernel.md):
 //
 //   * BOX PREFILTER.  The exact test of a (layer, quad) block costs 12 packed FP32 instructions
-//     = 24 FMA-pipe cycles per SM sub-partition, and 50-70% of the blocks are dead.  Per chunk
-//     the 64 (layer, quad) combinations are tested lane-parallel, bounding box of the layer's
-//     32 i against bounding box of the quad's 4 j (2 evaluations per lane + 2 ballots); only
-//     combinations whose boxes come within the cut-off run the exact test.  Quads with no live
-//     layer are not even loaded.
+//     = 24 FMA-pipe cycles per SM sub-partition, and 50-70% of the blocks are dead.  A chunk is
+//     128 staged j, one quad of 4 consecutive j per lane: each lane takes the bounding box of its
+//     own quad (no shuffles) and tests it against the bounding box of each layer's 32 i (4
+//     ballots per chunk); only combinations whose boxes come within the cut-off run the exact
+//     test, and the quad loop walks the set bits only, so dead quads cost nothing.
 //   * TYPE-HOMOGENEOUS j RUNS for per-type radii (MODE 1).  The j stream comes from a second
 //     copy of the positions sorted by (xy row, type, z cell, Morton): inside a sub-run every j
 //     has the same type, so cut2 / force value / 1/Reff of a pair depend on the lane only and
@@ -32,7 +32,7 @@
 #include "kernels_tile.cuh"
 
 #define T4_WARPS 4
-#define T4_JC 64
+#define T4_JC 128 // staged j per chunk and warp: one quad of 4 consecutive j per lane
 #define T4_MAXSUB (TK_MAX_RUNS * CF_T_MAX)
 #define T4_INF __int_as_float(0x7f800000)
 
@@ -134,22 +134,20 @@ __device__ __forceinline__ void t4_live(u64 dxa, u64 dya, u64 dza, u64 d2a, u64 
 // the table address from the packed types; MODE 1 reads (c2, A, B, cut2) of (layer, lane) from
 // shared memory per block.
 template <int MODE, bool WRAP>
-__device__ __forceinline__ void t4_chunk(unsigned sbase, int nquads, unsigned mask0, unsigned mask1,
-                                         const float (&npx)[TK_IPT], const float (&npy)[TK_IPT],
-                                         const float (&npz)[TK_IPT], unsigned tis4, unsigned s_tab_addr,
-                                         const float4* __restrict__ cst, float sx, float sy, float sz, float cutu,
-                                         float c2u, float pau, float pbu, T4AccScalar (&acc)[TK_IPT],
-                                         int (&cnt)[TK_IPT]) {
+__device__ __forceinline__ void t4_chunk(unsigned sbase, const unsigned (&live)[TK_IPT], const float (&npx)[TK_IPT],
+                                         const float (&npy)[TK_IPT], const float (&npz)[TK_IPT], unsigned tis4,
+                                         unsigned s_tab_addr, const float4* __restrict__ cst, float sx, float sy,
+                                         float sz, float cutu, float c2u, float pau, float pbu,
+                                         T4AccScalar (&acc)[TK_IPT], int (&cnt)[TK_IPT]) {
     const u64 sx2 = tk_pack(sx, sx), sy2 = tk_pack(sy, sy), sz2 = tk_pack(sz, sz);
     constexpr unsigned STRIDE = T4_WARPS * 2 * T4_JC * 4; // bytes between the x, y, z, t arrays
-    // bit 4*q + k of the 64-bit mask = (quad q, layer k) passed the box prefilter
-    unsigned long long m = ((unsigned long long)mask1 << 32) | mask0;
-    if (nquads < 16) m &= (1ull << (4 * nquads)) - 1ull;
-    unsigned qa = sbase;
+    // live[k] bit q = (quad q, layer k) passed the box prefilter; quads with no live layer cost nothing
+    unsigned any = live[0] | live[1] | live[2] | live[3];
 #pragma unroll 1
-    for (; m != 0ull; m >>= 4, qa += 16u) {
-        const unsigned m4 = (unsigned)m & 15u;
-        if (m4 == 0u) continue; // no layer's box comes near this quad's box
+    while (any) {
+        const unsigned bit = any & (0u - any);
+        any ^= bit;
+        const unsigned qa = sbase + 16u * (unsigned)(__ffs(bit) - 1);
         float4 X, Y, Z;
         int4 Tq = make_int4(0, 0, 0, 0);
         asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(X.x), "=f"(X.y), "=f"(X.z), "=f"(X.w) : "r"(qa));
@@ -162,7 +160,7 @@ __device__ __forceinline__ void t4_chunk(unsigned sbase, int nquads, unsigned ma
         const u64 za = tk_pack(Z.x, Z.y), zb = tk_pack(Z.z, Z.w);
 #pragma unroll
         for (int k = 0; k < TK_IPT; k++) {
-            if (!(m4 & (1u << k))) continue; // warp-uniform
+            if (!(live[k] & bit)) continue; // warp-uniform
             float4 cs = make_float4(c2u, pau, pbu, cutu);
             if (MODE == 1) cs = cst[k * 32];
             const u64 px = tk_pack(npx[k], npx[k]), py = tk_pack(npy[k], npy[k]), pz = tk_pack(npz[k], npz[k]);
@@ -224,7 +222,6 @@ force_tile4_kernel(const float4* __restrict__ pos4, const int* __restrict__ cell
     const unsigned s_tab_addr = (unsigned)__cvta_generic_to_shared(s_tab);
     const unsigned stage_addr = (unsigned)__cvta_generic_to_shared(&sm.x[warp][0][0]); // + buf*256 + 4*slot
     constexpr unsigned STRIDE = T4_WARPS * 2 * T4_JC * 4;
-    const int kk = lane & 3; // the layer this lane tests in the box prefilter
 
     for (;;) {
         int tile = 0;
@@ -325,54 +322,43 @@ force_tile4_kernel(const float4* __restrict__ pos4, const int* __restrict__ cell
         }                                           \
     } while (0)
         T4_ADVANCE();
-        float4 q0 = make_float4(TK_FAR, TK_FAR, TK_FAR, 0.f), q1 = q0;
-        if (have && off + lane < end) q0 = posj[off + lane];
-        if (have && off + 32 + lane < end) q1 = posj[off + 32 + lane];
         int cur_si = -1, buf = 0;
         float sx = 0.f, sy = 0.f, sz = 0.f;
         bool wrap = false;
         while (have) {
             const int csi = si, coff = off, cend = end;
-            // publish the chunk
+            // ---- load and publish the chunk: lane l holds the quad j = coff + 4l .. 4l+3 ----
             const unsigned sbase = stage_addr + (unsigned)buf * (T4_JC * 4);
+            float lox = T4_INF, loy = T4_INF, loz = T4_INF, hix = -T4_INF, hiy = -T4_INF, hiz = -T4_INF;
             {
-                const unsigned a = sbase + 4u * (unsigned)lane;
-                asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(q0.x));
-                asm volatile("st.shared.f32 [%0], %1;" ::"r"(a + STRIDE), "f"(q0.y));
-                asm volatile("st.shared.f32 [%0], %1;" ::"r"(a + 2 * STRIDE), "f"(q0.z));
-                asm volatile("st.shared.f32 [%0], %1;" ::"r"(a + 128u), "f"(q1.x));
-                asm volatile("st.shared.f32 [%0], %1;" ::"r"(a + 128u + STRIDE), "f"(q1.y));
-                asm volatile("st.shared.f32 [%0], %1;" ::"r"(a + 128u + 2 * STRIDE), "f"(q1.z));
+                float4 q[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int j = coff + 4 * lane + u;
+                    q[u] = j < cend ? posj[j] : make_float4(TK_FAR, TK_FAR, TK_FAR, 0.f);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) { // bounding box of the quad (valid j only)
+                    const bool v = coff + 4 * lane + u < cend;
+                    lox = fminf(lox, v ? q[u].x : T4_INF), hix = fmaxf(hix, v ? q[u].x : -T4_INF);
+                    loy = fminf(loy, v ? q[u].y : T4_INF), hiy = fmaxf(hiy, v ? q[u].y : -T4_INF);
+                    loz = fminf(loz, v ? q[u].z : T4_INF), hiz = fmaxf(hiz, v ? q[u].z : -T4_INF);
+                }
+                const unsigned a = sbase + 16u * (unsigned)lane;
+                asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a), "f"(q[0].x), "f"(q[1].x), "f"(q[2].x), "f"(q[3].x));
+                asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a + STRIDE), "f"(q[0].y), "f"(q[1].y), "f"(q[2].y), "f"(q[3].y));
+                asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a + 2 * STRIDE), "f"(q[0].z), "f"(q[1].z), "f"(q[2].z), "f"(q[3].z));
                 if (MODE == 0) {
-                    asm volatile("st.shared.s32 [%0], %1;" ::"r"(a + 3 * STRIDE), "r"((int)__float_as_uint(q0.w) * (T * 4)));
-                    asm volatile("st.shared.s32 [%0], %1;" ::"r"(a + 128u + 3 * STRIDE), "r"((int)__float_as_uint(q1.w) * (T * 4)));
+                    const int rb = T * 4; // bytes per tj row of s_tab
+                    asm volatile("st.shared.v4.s32 [%0], {%1,%2,%3,%4};" ::"r"(a + 3 * STRIDE),
+                                 "r"((int)__float_as_uint(q[0].w) * rb), "r"((int)__float_as_uint(q[1].w) * rb),
+                                 "r"((int)__float_as_uint(q[2].w) * rb), "r"((int)__float_as_uint(q[3].w) * rb));
                 }
             }
-            // bounding boxes of the quads: 4 consecutive lanes hold one quad of each half
-            const bool v0 = coff + lane < cend, v1 = coff + 32 + lane < cend;
-            float l0x = v0 ? q0.x : T4_INF, l0y = v0 ? q0.y : T4_INF, l0z = v0 ? q0.z : T4_INF;
-            float h0x = v0 ? q0.x : -T4_INF, h0y = v0 ? q0.y : -T4_INF, h0z = v0 ? q0.z : -T4_INF;
-            float l1x = v1 ? q1.x : T4_INF, l1y = v1 ? q1.y : T4_INF, l1z = v1 ? q1.z : T4_INF;
-            float h1x = v1 ? q1.x : -T4_INF, h1y = v1 ? q1.y : -T4_INF, h1z = v1 ? q1.z : -T4_INF;
-#pragma unroll
-            for (int o = 1; o <= 2; o <<= 1) {
-                l0x = fminf(l0x, __shfl_xor_sync(0xffffffffu, l0x, o));
-                l0y = fminf(l0y, __shfl_xor_sync(0xffffffffu, l0y, o));
-                l0z = fminf(l0z, __shfl_xor_sync(0xffffffffu, l0z, o));
-                h0x = fmaxf(h0x, __shfl_xor_sync(0xffffffffu, h0x, o));
-                h0y = fmaxf(h0y, __shfl_xor_sync(0xffffffffu, h0y, o));
-                h0z = fmaxf(h0z, __shfl_xor_sync(0xffffffffu, h0z, o));
-                l1x = fminf(l1x, __shfl_xor_sync(0xffffffffu, l1x, o));
-                l1y = fminf(l1y, __shfl_xor_sync(0xffffffffu, l1y, o));
-                l1z = fminf(l1z, __shfl_xor_sync(0xffffffffu, l1z, o));
-                h1x = fmaxf(h1x, __shfl_xor_sync(0xffffffffu, h1x, o));
-                h1y = fmaxf(h1y, __shfl_xor_sync(0xffffffffu, h1y, o));
-                h1z = fmaxf(h1z, __shfl_xor_sync(0xffffffffu, h1z, o));
-            }
             __syncwarp();
-            // the next chunk (possibly of the next run)
+            // the next chunk (possibly of the next run): prefetch hint, 128 float4 = 2 KiB <= 17 lines
             T4_ADVANCE();
-            if (have && lane < 9) { // 64 float4 = 1 KiB: at most 9 lines of 128 B
+            if (have && lane < 17) {
                 const float4* pf = posj + min(off + 8 * lane, end - 1);
                 asm volatile("prefetch.global.L1 [%0];" ::"l"(pf));
             }
@@ -399,37 +385,25 @@ force_tile4_kernel(const float4* __restrict__ pos4, const int* __restrict__ cell
                     __syncwarp();
                 }
             }
-            // box prefilter: lane tests quad (lane>>2) of each half against layer kk = lane&3
-            unsigned mask0, mask1;
-            {
-                const float4 b0 = sm.box[warp][kk][0], b1 = sm.box[warp][kk][1];
-                const float blo[3] = {b0.x, b0.y, b0.z}, bhi[3] = {b1.x, b1.y, b1.z};
-                const float tA = b0.w;
-                float gx = fmaxf(fmaxf((l0x - bhi[0]) + sx, (blo[0] - h0x) - sx), 0.f);
-                float gy = fmaxf(fmaxf((l0y - bhi[1]) + sy, (blo[1] - h0y) - sy), 0.f);
-                float gz = fmaxf(fmaxf((l0z - bhi[2]) + sz, (blo[2] - h0z) - sz), 0.f);
-                mask0 = __ballot_sync(0xffffffffu, fmaf(gz, gz, fmaf(gx, gx, gy * gy)) < tA);
-                gx = fmaxf(fmaxf((l1x - bhi[0]) + sx, (blo[0] - h1x) - sx), 0.f);
-                gy = fmaxf(fmaxf((l1y - bhi[1]) + sy, (blo[1] - h1y) - sy), 0.f);
-                gz = fmaxf(fmaxf((l1z - bhi[2]) + sz, (blo[2] - h1z) - sz), 0.f);
-                mask1 = __ballot_sync(0xffffffffu, fmaf(gz, gz, fmaf(gx, gx, gy * gy)) < tA);
+            // ---- box prefilter: every lane tests its own quad against the box of each layer ----
+            unsigned live[TK_IPT];
+#pragma unroll
+            for (int k = 0; k < TK_IPT; k++) {
+                const float4 b0 = sm.box[warp][k][0], b1 = sm.box[warp][k][1]; // broadcast reads
+                const float gx = fmaxf(fmaxf((lox - b1.x) + sx, (b0.x - hix) - sx), 0.f);
+                const float gy = fmaxf(fmaxf((loy - b1.y) + sy, (b0.y - hiy) - sy), 0.f);
+                const float gz = fmaxf(fmaxf((loz - b1.z) + sz, (b0.z - hiz) - sz), 0.f);
+                live[k] = __ballot_sync(0xffffffffu, fmaf(gz, gz, fmaf(gx, gx, gy * gy)) < b0.w);
             }
-            if (mask0 | mask1) {
-                const int nquads = (min(T4_JC, cend - coff) + 3) >> 2;
+            if (live[0] | live[1] | live[2] | live[3]) {
                 if (wrap)
-                    t4_chunk<MODE, true>(sbase, nquads, mask0, mask1, npx, npy, npz, tis4, s_tab_addr, wcst, sx, sy, sz,
-                                         cutu, c2u, pau, pbu, acc, cnt);
+                    t4_chunk<MODE, true>(sbase, live, npx, npy, npz, tis4, s_tab_addr, wcst, sx, sy, sz, cutu, c2u, pau, pbu,
+                                         acc, cnt);
                 else
-                    t4_chunk<MODE, false>(sbase, nquads, mask0, mask1, npx, npy, npz, tis4, s_tab_addr, wcst, sx, sy, sz,
-                                          cutu, c2u, pau, pbu, acc, cnt);
+                    t4_chunk<MODE, false>(sbase, live, npx, npy, npz, tis4, s_tab_addr, wcst, sx, sy, sz, cutu, c2u, pau,
+                                          pbu, acc, cnt);
             }
             buf ^= 1; // the other buffer was last read one chunk ago by this same warp
-            if (have) { // the next chunk: an L1 hit after the prefetch hint
-                q0 = make_float4(TK_FAR, TK_FAR, TK_FAR, 0.f);
-                q1 = q0;
-                if (off + lane < end) q0 = posj[off + lane];
-                if (off + 32 + lane < end) q1 = posj[off + 32 + lane];
-            }
         }
 #undef T4_ADVANCE
 
