@@ -250,10 +250,12 @@ def run_ours(args):
         "kernel": "pair_force", "bound": "fp32", "achieved": round(achieved, 3), "peak": round(tf.value, 2),
         "unit": "TFLOP/s", "frac": round(achieved / tf.value, 4) if tf.value else None, "traffic": traffic,
         "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full)",
-        "algorithmic_bytes_per_launch": 32 * n,
+        "algorithmic_bytes_per_launch": 32 * n,  # read pos4 16 B + write frc4 16 B per particle
         "peak_source": "FFMA microbenchmark measured in this run (no FP32 figure in MEASURED_PEAKS.json)",
         "flops_per_accepted_pair": 37, "accepted_pairs_per_step": accepted, "tested_pairs_per_step": tested,
         "pair_tests_per_s": round(tested / (force_ms * 1e-3), 1) if force_ms > 0 else None,
+        "tested_pairs_note": "pairs covered by the 27-cell stencil; the generation-4 kernel's box prefilter "
+                             "decides about half of them without the exact per-pair test",
         "kernel_ms": round(force_ms, 4),
         "hbm_kernels": {
             "integrate": {"bytes_per_particle": 96, "ms": round(integ_ms, 4),
