@@ -606,7 +606,7 @@ extern "C" int cf_destroy(cf_sim* s) {
         double c = (double)(g_slab_times.calls - 5);
         fprintf(stderr, "[cellflow_b200 rank %d] slab build x%lld: host total %.3f ms (wait own sort %.3f, wait migrants %.3f); "
                         "device: migrant exchange %.3f ms, merge+reorder+bounds %.3f ms, halo exchange %.3f ms\n",
-                s->rank, g_slab_times.calls, 1e3 * g_slab_times.enqueue / c, 1e3 * g_slab_times.sort_sync / c,
+                s->rank, g_slab_times.calls, 1e3 * g_slab_times.enqueue / c, 0.0,
                 1e3 * g_slab_times.mig_sync / c, g_slab_times.gpu_mig / c, g_slab_times.gpu_mid / c, g_slab_times.gpu_halo / c);
     }
     slab_free(s);
@@ -1190,17 +1190,18 @@ extern "C" int cf_build_graph(cf_sim* s, float dist, int max_conn, int* n_edges)
     if (int rc = build_cell_list(s)) return rc;
     // ---- slots that take part: owned, plus ghost layers that are real neighbours (not the seam) ----
     int first = s->base, count = s->n;
+    int use_lo_ghost = 0, use_hi_ghost = 0;
     float ext_lo[3] = {0.f, 0.f, 0.f};
     float ext_hi[3] = {s->sc.W[0], s->sc.W[1], s->sc.W[2]};
     if (s->slab) {
         float ex = (s->sc.W[0] / (float)s->world) / (float)s->nxl;
         if ((double)dist * (1.0 + 1e-5) > (double)ex)
             return fail(CF_ERR_ARG, "proximity distance %.1f exceeds the one-cell ghost layer (%.1f) of slab mode", dist, ex);
-        int g[2] = {0, 0};
-        CU(cudaMemcpyAsync(g, s->d_slab_counts + 4, 2 * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
-        CU(cudaStreamSynchronize(s->stream));
-        if (s->rank > 0) first -= g[0], count += g[0];
-        if (s->rank < s->world - 1) count += g[1];
+        // every slot that can hold a particle; the key kernel reads the ghost extents on the device
+        use_lo_ghost = s->rank > 0, use_hi_ghost = s->rank < s->world - 1;
+        first = use_lo_ghost ? std::max(0, s->base - slab_halo_msg_cap(s)) : s->base;
+        int last = std::min(s->cap, s->base + s->n + (use_hi_ghost ? slab_halo_msg_cap(s) : 0));
+        count = last - first;
         ext_lo[0] = s->geom.x_lo - ex;
         ext_hi[0] = s->geom.x_hi + ex;
     }
@@ -1250,7 +1251,8 @@ extern "C" int cf_build_graph(cf_sim* s, float dist, int max_conn, int* n_edges)
             s->gstart_cap = (size_t)nkeys + 2 + (size_t)nkeys / 4;
             CU(cudaMalloc(&s->gstart, s->gstart_cap * sizeof(int)));
         }
-        LAUNCH(s, graph_key_kernel, div_up(count, 256), 256, 0, s->pos[s->cur], first, count, g, s->gk[0], s->gv[0]);
+        LAUNCH(s, graph_key_kernel, div_up(count, 256), 256, 0, s->pos[s->cur], first, count, g, s->cell_start, s->ncell,
+               s->base, s->n, use_lo_ghost, use_hi_ghost, s->gk[0], s->gv[0]);
         int src = 0;
         if (int rc = radix_sort_pairs(s, s->gk, s->gv, count, (long long)nkeys + 1, &src)) return rc;
         LAUNCH(s, graph_gather_kernel, div_up(count, 256), 256, 0, s->gv[src], s->pos[s->cur], s->id[s->cur], count, s->gpos);

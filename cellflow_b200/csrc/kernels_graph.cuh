@@ -32,21 +32,32 @@ __device__ __forceinline__ int graph_coord(float x, float org, float inv, int n)
 }
 
 // key = type * ncell + cell for every slot in [first, first + n); excluded slots get the end key.
+// Slots that take part are [lo, hi): the owned range [own_first, own_first + own_n), extended by
+// the low / high ghost layer when it is a real neighbour (not the periodic seam).  The ghost
+// extents are read from the cell list on the device (cell_start[0], cell_start[ncell]), so the
+// host never has to wait for the ghost counts.
 __global__ void graph_key_kernel(const float4* __restrict__ pos4, int first, int n, GraphGrid g,
-                                 uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+                                 const int* __restrict__ cell_start, int ncell, int own_first, int own_n,
+                                 int use_lo_ghost, int use_hi_ghost, uint32_t* __restrict__ keys,
+                                 uint32_t* __restrict__ vals) {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
-    float4 p = pos4[first + k];
-    uint32_t t = __float_as_uint(p.w);
+    const int slot = first + k;
+    const int lo = use_lo_ghost ? cell_start[0] : own_first;
+    const int hi = use_hi_ghost ? cell_start[ncell] : own_first + own_n;
     uint32_t key = (uint32_t)g.T * (uint32_t)g.ncell; // "not gridded"
-    if (t < (uint32_t)g.T && p.x >= g.x_min && p.x < g.x_max) {
-        int cx = graph_coord(p.x, g.org[0], g.inv[0], g.dims[0]);
-        int cy = graph_coord(p.y, g.org[1], g.inv[1], g.dims[1]);
-        int cz = graph_coord(p.z, g.org[2], g.inv[2], g.dims[2]);
-        key = t * (uint32_t)g.ncell + (uint32_t)((cx * g.dims[1] + cy) * g.dims[2] + cz);
+    if (slot >= lo && slot < hi) {
+        float4 p = pos4[slot];
+        uint32_t t = __float_as_uint(p.w);
+        if (t < (uint32_t)g.T && p.x >= g.x_min && p.x < g.x_max) {
+            int cx = graph_coord(p.x, g.org[0], g.inv[0], g.dims[0]);
+            int cy = graph_coord(p.y, g.org[1], g.inv[1], g.dims[1]);
+            int cz = graph_coord(p.z, g.org[2], g.inv[2], g.dims[2]);
+            key = t * (uint32_t)g.ncell + (uint32_t)((cx * g.dims[1] + cy) * g.dims[2] + cz);
+        }
     }
     keys[k] = key;
-    vals[k] = (uint32_t)(first + k);
+    vals[k] = (uint32_t)slot;
 }
 
 // Positions in graph order with the original id in .w, so the candidate loop is one 16-byte load.

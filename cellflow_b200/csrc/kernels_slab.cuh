@@ -82,11 +82,15 @@ __global__ void slab_class_counts_kernel(const uint32_t* __restrict__ skeys, int
     }
 }
 
-// Gather the two leaver tails (sorted order) into the send messages.
+// Gather the two leaver tails (sorted order) into the send messages.  The class counts are read
+// from device memory (counts[0..2] = stay, left, right), so the host does not have to wait for
+// them before the exchange is enqueued; a count above the message capacity is clamped here and
+// reported by the host after its (single) synchronisation.
 __global__ void slab_pack_migrants_kernel(const uint32_t* __restrict__ perm, const float4* __restrict__ pos4,
                                           const float4* __restrict__ vel4, const int* __restrict__ id,
-                                          int n_stay, int n_left, int n_right, char* __restrict__ msg_left,
+                                          const int* __restrict__ counts, char* __restrict__ msg_left,
                                           char* __restrict__ msg_right, int cap) {
+    const int n_stay = counts[0], n_left = min(counts[1], cap), n_right = min(counts[2], cap);
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k == 0) {
         *mig_count(msg_left, cap) = n_left;
@@ -95,7 +99,7 @@ __global__ void slab_pack_migrants_kernel(const uint32_t* __restrict__ perm, con
     if (k >= n_left + n_right) return;
     char* msg = k < n_left ? msg_left : msg_right;
     int m = k < n_left ? k : k - n_left;
-    uint32_t src = perm[n_stay + k];
+    uint32_t src = perm[n_stay + (k < n_left ? k : counts[1] + (k - n_left))];
     mig_pos(msg, cap)[m] = pos4[src];
     mig_vel(msg, cap)[m] = vel4[src];
     mig_id(msg, cap)[m] = id[src];

@@ -197,29 +197,20 @@ static int ensure_sorted_slab(cf_sim* s, cudaEvent_t ev_x0, cudaEvent_t ev_x1) {
     } else {
         CU(cudaMemsetAsync(s->d_slab_counts, 0, 3 * sizeof(int), s->stream));
     }
-    CU(cudaMemcpyAsync(s->h_slab_counts, s->d_slab_counts, 4 * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
-    const double t_s0 = wall_now();
-    CU(cudaStreamSynchronize(s->stream));
-    if (g_slab_times.calls >= 5) g_slab_times.sort_sync += wall_now() - t_s0;
-    if (int rc = slab_check_flags(s)) return rc;
-    n_stay = s->h_slab_counts[0], n_left = s->h_slab_counts[1], n_right = s->h_slab_counts[2];
     const int mcap = slab_mig_msg_cap(s), hcap = slab_halo_msg_cap(s);
-    if (n_left > mcap || n_right > mcap)
-        return fail(CF_ERR_CAPACITY, "%d/%d migrants exceed the migrant message capacity (%d): raise migrant_slack",
-                    n_left, n_right, mcap);
-
     if (ev_x0) CU(cudaEventRecord(ev_x0, s->stream));
     const bool dbg = getenv("CF_SLAB_DEBUG") != nullptr;
     if (dbg && !g_slab_times.ev[0])
         for (int i = 0; i < 4; i++) cudaEventCreate(&g_slab_times.ev[i]);
     if (dbg) cudaEventRecord(g_slab_times.ev[0], s->stream);
-    // ---- migrants ----
-    LAUNCH(s, slab_pack_migrants_kernel, div_up(std::max(n_left + n_right, 1), 256), 256, 0, s->vals[src],
-           s->pos[cur] + B, s->vel[cur] + B, s->id[cur] + B, n_stay, n_left, n_right, s->send_mig[0], s->send_mig[1],
-           mcap);
+    // ---- migrants: packed with device-side counts, so nothing waits for the host here ----
+    LAUNCH(s, slab_pack_migrants_kernel, div_up(2 * mcap, 256), 256, 0, s->vals[src], s->pos[cur] + B, s->vel[cur] + B,
+           s->id[cur] + B, s->d_slab_counts, s->send_mig[0], s->send_mig[1], mcap);
     if (int rc = slab_exchange(s, s->send_mig[0], s->send_mig[1], s->recv_mig[0], s->recv_mig[1],
                                slab_mig_bytes(mcap)))
         return rc;
+    // the only host synchronisation of the cell-list build: class counts + arrival counts
+    CU(cudaMemcpyAsync(s->h_slab_counts, s->d_slab_counts, 4 * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
     CU(cudaMemcpyAsync(&s->h_slab_counts[6], mig_count(s->recv_mig[0], mcap), sizeof(int),
                        cudaMemcpyDeviceToHost, s->stream));
     CU(cudaMemcpyAsync(&s->h_slab_counts[7], mig_count(s->recv_mig[1], mcap), sizeof(int),
@@ -228,6 +219,11 @@ static int ensure_sorted_slab(cf_sim* s, cudaEvent_t ev_x0, cudaEvent_t ev_x1) {
     const double t_s1 = wall_now();
     CU(cudaStreamSynchronize(s->stream));
     if (g_slab_times.calls >= 5) g_slab_times.mig_sync += wall_now() - t_s1;
+    if (int rc = slab_check_flags(s)) return rc;
+    n_stay = s->h_slab_counts[0], n_left = s->h_slab_counts[1], n_right = s->h_slab_counts[2];
+    if (n_left > mcap || n_right > mcap)
+        return fail(CF_ERR_CAPACITY, "%d/%d migrants exceed the migrant message capacity (%d): raise migrant_slack",
+                    n_left, n_right, mcap);
     const int n_al = s->h_slab_counts[6], n_ar = s->h_slab_counts[7], n_a = n_al + n_ar;
     const int n_new = n_stay + n_a;
     if (n + n_a > s->cap_own || n_new > s->cap_own)
