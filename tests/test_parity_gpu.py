@@ -75,6 +75,34 @@ def test_step_parity(name, n, mode, over, radio, kernel):
     check_step(p, table, radio, state, counts, force_kernel=kernel)
 
 
+@pytest.mark.parametrize("kernel", [1, 2, 3])
+def test_ten_types_random_radii(kernel):
+    """MAX_PARTICLE_TYPES = 10 (SimulationParams.h:64) with a different radius modifier per type and
+    a dense state: 180 (run, type) sub-runs per tile in the generation-4 kernel, asymmetric 10x10
+    force matrix."""
+    rng = np.random.default_rng(2024)
+    T = 10
+    p, _, _ = U.config("eater", numParticleTypes=T, ratioWithLFO=0.8, canvasWidth=3000.0, canvasHeight=2600.0,
+                       canvasDepth=2200.0, radius=180.0)
+    table = O.force_table(rng.uniform(-1, 1, T * T).astype(np.float32), T, p.forceRange, p.forceBias, p.forceOffset)
+    radio = rng.uniform(-0.6, 1.0, T).astype(np.float32)
+    state, counts = U.random_state(60000, T, 7, p.canvas, "uniform")
+    check_step(p, table, radio, state, counts, force_kernel=kernel)
+
+
+def test_auto_kernel_choice_dense_mixed_radii():
+    """No force_kernel option: a dense state with per-type radii takes the generation-4 tile kernel
+    (type-sorted j copy), and the result still matches the oracle."""
+    p, table, _ = U.config("eater", ratioWithLFO=0.5, canvasWidth=2400.0, canvasHeight=2400.0, canvasDepth=2400.0)
+    radio = np.float32([1.0, 0.5, 0.0, 0.0, -0.5, 1.0])
+    state, counts = U.random_state(40000, 6, 11, p.canvas, "uniform")
+    sim = make_sim(p, table, radio, state, counts)
+    sim.simulate()
+    assert sim.stats().force_kernel == 3
+    sim.close()
+    check_step(p, table, radio, state, counts)
+
+
 def test_default_parameters_and_matrix():
     """README headline configuration: SimulationParams.h defaults, default (glibc rand) matrix."""
     p = O.Params()
