@@ -151,7 +151,7 @@ def dist_env():
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
-GRAPH_PRIME_STEPS = 6
+GRAPH_PRIME_STEPS = 8
 
 
 def run_ours(args):
@@ -180,6 +180,8 @@ def run_ours(args):
     sim.initializeParticles(seed=seed, mode=mode)
     if args.force_kernel:
         sim.setOption("force_kernel", args.force_kernel)
+    if args.graph_kernel:
+        sim.setOption("graph_kernel", args.graph_kernel)
     if args.no_graphs:
         sim.setOption("cuda_graphs", 0)
     sim.setOption("timing", 2)   # whole-step events; the step itself replays a CUDA graph
@@ -440,6 +442,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--force-kernel", type=int, default=0, help="0 auto, 1 per-particle, 2 tile (generation 3), 3 tile (generation 4)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--graph-kernel", type=int, default=0, help="0 auto, 1 thread per particle, 2 warp per particle")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-graphs", action="store_true", help="launch every kernel individually")
     ap.add_argument("--ref-cpu", action="store_true", help="reference arm on the CPU oracle port instead")

@@ -110,6 +110,11 @@ struct cf_sim {
     size_t graph_cap = 0;
     int* gstart = nullptr;
     size_t gstart_cap = 0;
+    unsigned long long* d_graph_occ = nullptr; // sum over (type, cell) keys of occupancy^2, last build
+    unsigned long long h_graph_occ = 0;
+    double graph_mean_occ = 0.0;               // mean same-key companions per particle, last build
+    int opt_graph_kernel = 0;                  // 0 auto, 1 thread per particle, 2 warp per particle
+    int last_graph_kernel = 0;
 
     // tile kernel
     int2* d_tiles = nullptr;
@@ -159,6 +164,7 @@ struct cf_sim {
         bool swap_keys = false;
     };
     StepGraph step_graphs[4];
+    StepGraph graph_graphs[4]; // cf_build_graph's device sequence (single GPU)
     int opt_graphs = 1;
 
     // options
@@ -577,6 +583,7 @@ extern "C" int cf_create(int particle_count, int num_types, int device, cf_sim**
     int rc = alloc_particle_buffers(s, particle_count);
     if (rc == 0 && cudaMalloc(&s->d_tables, sizeof(DeviceTables)) != cudaSuccess) rc = fail(CF_ERR_CUDA, "cudaMalloc tables");
     if (rc == 0 && cudaMalloc(&s->d_edge_count, sizeof(int)) != cudaSuccess) rc = fail(CF_ERR_CUDA, "cudaMalloc");
+    if (rc == 0 && cudaMalloc(&s->d_graph_occ, sizeof(unsigned long long)) != cudaSuccess) rc = fail(CF_ERR_CUDA, "cudaMalloc");
     if (rc == 0 && cudaMalloc(&s->d_tile_ctrl, 2 * sizeof(int)) != cudaSuccess) rc = fail(CF_ERR_CUDA, "cudaMalloc");
     if (rc == 0 && cudaMalloc(&s->d_half, CF_T_MAX * sizeof(float)) != cudaSuccess) rc = fail(CF_ERR_CUDA, "cudaMalloc");
     if (rc == 0) {
@@ -602,6 +609,8 @@ extern "C" int cf_destroy(cf_sim* s) {
     if (s->stream) cudaStreamSynchronize(s->stream);
     for (auto& g : s->step_graphs)
         if (g.exec) cudaGraphExecDestroy(g.exec);
+    for (auto& g : s->graph_graphs)
+        if (g.exec) cudaGraphExecDestroy(g.exec);
     if (s->slab && getenv("CF_SLAB_DEBUG") && g_slab_times.calls > 5) {
         double c = (double)(g_slab_times.calls - 5);
         fprintf(stderr, "[cellflow_b200 rank %d] slab build x%lld: host total %.3f ms (wait own sort %.3f, wait migrants %.3f); "
@@ -615,6 +624,7 @@ extern "C" int cf_destroy(cf_sim* s) {
     cudaFree(s->cell_start);
     cudaFree(s->d_tables);
     cudaFree(s->d_edge_count);
+    cudaFree(s->d_graph_occ);
     cudaFree(s->d_accum);
     cudaFree(s->d_tiles);
     for (int b = 0; b < 2; b++) cudaFree(s->gk[b]), cudaFree(s->gv[b]);
@@ -1165,6 +1175,182 @@ extern "C" int cf_step_host(cf_sim* s, const cf_params* p, const cf_particle* in
 // ---------------------------------------------------------------------------------------------
 // proximity graph
 // ---------------------------------------------------------------------------------------------
+// Everything cf_build_graph launches depends on this plan (plus the buffers and the step constants).
+struct GraphPlan {
+    int first, count;            // slots [first, first + count) are keyed
+    int use_lo_ghost, use_hi_ghost;
+    int nkeys, mc, gkernel;
+    float dist2;
+    GraphGrid g;
+};
+
+static int graph_make_plan(cf_sim* s, float dist, int mc, GraphPlan& P) {
+    memset(&P, 0, sizeof(P));
+    // ---- slots that take part: owned, plus ghost layers that are real neighbours (not the seam) ----
+    P.first = s->base, P.count = s->n;
+    float ext_lo[3] = {0.f, 0.f, 0.f};
+    float ext_hi[3] = {s->sc.W[0], s->sc.W[1], s->sc.W[2]};
+    if (s->slab) {
+        float ex = (s->sc.W[0] / (float)s->world) / (float)s->nxl;
+        if ((double)dist * (1.0 + 1e-5) > (double)ex)
+            return fail(CF_ERR_ARG, "proximity distance %.1f exceeds the one-cell ghost layer (%.1f) of slab mode", dist, ex);
+        // every slot that can hold a particle; the key kernel reads the ghost extents on the device
+        P.use_lo_ghost = s->rank > 0, P.use_hi_ghost = s->rank < s->world - 1;
+        P.first = P.use_lo_ghost ? std::max(0, s->base - slab_halo_msg_cap(s)) : s->base;
+        int last = std::min(s->cap, s->base + s->n + (P.use_hi_ghost ? slab_halo_msg_cap(s) : 0));
+        P.count = last - P.first;
+        ext_lo[0] = s->geom.x_lo - ex;
+        ext_hi[0] = s->geom.x_hi + ex;
+    }
+    // ---- the graph's own (type, cell) list, cell edge >= dist ----
+    GraphGrid& g = P.g;
+    double edge = (double)dist * (1.0 + 1e-5), vol = 1.0;
+    for (int a = 0; a < 3; a++) vol *= (double)(ext_hi[a] - ext_lo[a]);
+    double max_keys = std::min(4.0 * std::max(P.count, 0) + 4096.0, 1.6e7);
+    edge = std::max(edge, cbrt(vol * s->T / max_keys));
+    long long nc = 1;
+    for (int a = 0; a < 3; a++) {
+        int d = (int)floor((double)(ext_hi[a] - ext_lo[a]) / edge);
+        d = std::max(1, std::min(d, 1024));
+        g.dims[a] = d;
+        g.org[a] = ext_lo[a];
+        g.inv[a] = (float)d / (ext_hi[a] - ext_lo[a]);
+        nc *= d;
+    }
+    g.ncell = (int)nc;
+    g.T = s->T;
+    g.x_min = -INFINITY;
+    g.x_max = INFINITY;
+    P.nkeys = s->T * g.ncell; // key nkeys = "not gridded"
+    P.mc = mc;
+    P.dist2 = dist * dist;
+    // kernel choice from the occupancy of the PREVIOUS build (read back with its edge count, so no
+    // extra synchronisation): ~27 * mean occupancy candidates per particle; above ~250 the
+    // warp-per-particle kernel wins (spawn cube, clustered states), below it thread-per-particle
+    P.gkernel = s->opt_graph_kernel;
+    if (P.gkernel == 0) P.gkernel = 27.0 * s->graph_mean_occ >= 250.0 ? 2 : 1;
+    return 0;
+}
+
+static int graph_ensure_buffers(cf_sim* s, const GraphPlan& P) {
+    const int count = P.count, nkeys = P.nkeys;
+    if ((size_t)count > s->graph_cap) {
+        CU(cudaStreamSynchronize(s->stream));
+        for (int b = 0; b < 2; b++) {
+            cudaFree(s->gk[b]);
+            cudaFree(s->gv[b]);
+            s->gk[b] = s->gv[b] = nullptr;
+        }
+        cudaFree(s->gpos);
+        s->gpos = nullptr;
+        s->graph_cap = (size_t)count + (size_t)count / 8 + 1024;
+        for (int b = 0; b < 2; b++) {
+            CU(cudaMalloc(&s->gk[b], s->graph_cap * sizeof(uint32_t)));
+            CU(cudaMalloc(&s->gv[b], s->graph_cap * sizeof(uint32_t)));
+        }
+        CU(cudaMalloc(&s->gpos, s->graph_cap * sizeof(float4)));
+    }
+    if ((size_t)nkeys + 2 > s->gstart_cap) {
+        CU(cudaStreamSynchronize(s->stream));
+        cudaFree(s->gstart);
+        s->gstart = nullptr;
+        s->gstart_cap = (size_t)nkeys + 2 + (size_t)nkeys / 4;
+        CU(cudaMalloc(&s->gstart, s->gstart_cap * sizeof(int)));
+    }
+    return 0;
+}
+
+// The device work of one graph build: (cell list of the current positions,) key, sort, gather,
+// bounds, occupancy, graph kernel.  No host synchronisation, no allocation: capturable.
+static int graph_device_sequence(cf_sim* s, const GraphPlan& P, bool with_cell_list) {
+    if (with_cell_list)
+        if (int rc = build_cell_list(s)) return rc;
+    CU(cudaMemsetAsync(s->d_edge_count, 0, sizeof(int), s->stream));
+    CU(cudaMemsetAsync(s->d_graph_occ, 0, sizeof(unsigned long long), s->stream));
+    if (!(P.count > 0 && s->n > 0)) return 0;
+    const int count = P.count, nkeys = P.nkeys;
+    LAUNCH(s, graph_key_kernel, div_up(count, 256), 256, 0, s->pos[s->cur], P.first, count, P.g, s->cell_start, s->ncell,
+           s->base, s->n, P.use_lo_ghost, P.use_hi_ghost, s->gk[0], s->gv[0]);
+    int src = 0;
+    if (int rc = radix_sort_pairs(s, s->gk, s->gv, count, (long long)nkeys + 1, &src)) return rc;
+    LAUNCH(s, graph_gather_kernel, div_up(count, 256), 256, 0, s->gv[src], s->pos[s->cur], s->id[s->cur], count, s->gpos);
+    LAUNCH(s, graph_bounds_kernel, div_up(nkeys + 1, 256), 256, 0, s->gk[src], count, s->gstart, nkeys);
+    LAUNCH(s, graph_occupancy_kernel, div_up(nkeys, 256), 256, 0, s->gstart, nkeys, s->d_graph_occ);
+    if (P.gkernel == 2)
+        LAUNCH(s, graph_warp_kernel, div_up(count, CF_GRAPHW_WARPS), CF_GRAPHW_WARPS * 32, 0, s->gpos, s->gv[src],
+               s->gk[src], s->gstart, count, s->base, s->n, P.g, P.dist2, P.mc, s->edges, s->edge_slots, s->edge_cap,
+               s->d_edge_count);
+    else
+        LAUNCH(s, graph_kernel, div_up(count, CF_GRAPH_THREADS), CF_GRAPH_THREADS,
+               (size_t)3 * 2 * P.mc * CF_GRAPH_THREADS * sizeof(int), s->gpos, s->gv[src], s->gk[src], s->gstart, count,
+               s->base, s->n, P.g, P.dist2, P.mc, s->edges, s->edge_slots, s->edge_cap, s->d_edge_count);
+    return 0;
+}
+
+// Single GPU: the sequence above is ~25 small launches, which is what a graph build costs at
+// 100 k particles; like the step it is run directly once per parameter set (buffers are sized),
+// captured into a CUDA graph the second time and replayed from the third.
+static int graph_sequence_cached(cf_sim* s, const GraphPlan& P) {
+    std::vector<char> sig = step_signature(s);
+    auto put = [&](const void* p, size_t n) { sig.insert(sig.end(), (const char*)p, (const char*)p + n); };
+    put(&P, sizeof(P));
+    const void* ptrs[] = {s->gk[0], s->gk[1], s->gv[0], s->gv[1], s->gpos, s->gstart, s->edges, s->edge_slots,
+                          s->d_edge_count, s->d_graph_occ};
+    put(ptrs, sizeof(ptrs));
+    put(&s->edge_cap, sizeof(s->edge_cap));
+    cf_sim::StepGraph* hit = nullptr;
+    cf_sim::StepGraph* seen = nullptr;
+    cf_sim::StepGraph* spare = nullptr;
+    for (auto& g : s->graph_graphs) {
+        if (g.exec && g.sig == sig) hit = &g;
+        else if (!g.exec && g.seen == sig) seen = &g;
+        else if (!g.exec && g.seen.empty() && !spare) spare = &g;
+    }
+    const bool was_sorted = s->sorted_valid;
+    if (hit) {
+        CU(cudaGraphLaunch(hit->exec, s->stream));
+        if (!was_sorted) { // what ensure_sorted does on the host
+            if (hit->swap_keys) std::swap(s->keys[0], s->keys[1]), std::swap(s->vals[0], s->vals[1]);
+            s->cur ^= 1;
+        }
+        s->sorted_valid = true;
+        s->launches += hit->nodes;
+        return 0;
+    }
+    if (seen) {
+        uint32_t* k0 = s->keys[0];
+        long long before = s->launches;
+        CU(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
+        int rc = graph_device_sequence(s, P, true);
+        cudaGraph_t graph = nullptr;
+        cudaError_t e = cudaStreamEndCapture(s->stream, &graph);
+        if (rc) {
+            if (graph) cudaGraphDestroy(graph);
+            return rc;
+        }
+        if (e != cudaSuccess) return fail(CF_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
+        e = cudaGraphInstantiate(&seen->exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) return fail(CF_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e));
+        seen->sig = sig;
+        seen->seen.clear();
+        seen->nodes = s->launches - before;
+        seen->swap_keys = s->keys[0] != k0;
+        CU(cudaGraphLaunch(seen->exec, s->stream)); // the capture recorded, it did not run
+        return 0;
+    }
+    if (!spare) {
+        for (auto& g : s->graph_graphs) {
+            if (g.exec) cudaGraphExecDestroy(g.exec);
+            g = cf_sim::StepGraph();
+        }
+        spare = &s->graph_graphs[0];
+    }
+    int rc = graph_device_sequence(s, P, true);
+    spare->seen = sig;
+    return rc;
+}
+
 extern "C" int cf_build_graph(cf_sim* s, float dist, int max_conn, int* n_edges) {
     ARG(s && n_edges);
     *n_edges = 0;
@@ -1187,87 +1373,28 @@ extern "C" int cf_build_graph(cf_sim* s, float dist, int max_conn, int* n_edges)
         s->edge_cap = (int)need;
     }
     if (s->opt_timing) CU(cudaEventRecord(s->ev_g0, s->stream));
-    if (int rc = build_cell_list(s)) return rc;
-    // ---- slots that take part: owned, plus ghost layers that are real neighbours (not the seam) ----
-    int first = s->base, count = s->n;
-    int use_lo_ghost = 0, use_hi_ghost = 0;
-    float ext_lo[3] = {0.f, 0.f, 0.f};
-    float ext_hi[3] = {s->sc.W[0], s->sc.W[1], s->sc.W[2]};
+    GraphPlan P;
     if (s->slab) {
-        float ex = (s->sc.W[0] / (float)s->world) / (float)s->nxl;
-        if ((double)dist * (1.0 + 1e-5) > (double)ex)
-            return fail(CF_ERR_ARG, "proximity distance %.1f exceeds the one-cell ghost layer (%.1f) of slab mode", dist, ex);
-        // every slot that can hold a particle; the key kernel reads the ghost extents on the device
-        use_lo_ghost = s->rank > 0, use_hi_ghost = s->rank < s->world - 1;
-        first = use_lo_ghost ? std::max(0, s->base - slab_halo_msg_cap(s)) : s->base;
-        int last = std::min(s->cap, s->base + s->n + (use_hi_ghost ? slab_halo_msg_cap(s) : 0));
-        count = last - first;
-        ext_lo[0] = s->geom.x_lo - ex;
-        ext_hi[0] = s->geom.x_hi + ex;
+        // the cell-list build migrates particles (and synchronises with the host): plan afterwards
+        if (int rc = build_cell_list(s)) return rc;
+        if (int rc = graph_make_plan(s, dist, mc, P)) return rc;
+        if (int rc = graph_ensure_buffers(s, P)) return rc;
+        if (int rc = graph_device_sequence(s, P, false)) return rc;
+    } else {
+        if (int rc = graph_make_plan(s, dist, mc, P)) return rc;
+        if (int rc = graph_ensure_buffers(s, P)) return rc;
+        if (int rc = s->opt_graphs ? graph_sequence_cached(s, P) : graph_device_sequence(s, P, true)) return rc;
     }
-    CU(cudaMemsetAsync(s->d_edge_count, 0, sizeof(int), s->stream));
-    if (count > 0 && s->n > 0) {
-        // ---- the graph's own (type, cell) list, cell edge >= dist ----
-        GraphGrid g;
-        memset(&g, 0, sizeof(g));
-        double edge = (double)dist * (1.0 + 1e-5), vol = 1.0;
-        for (int a = 0; a < 3; a++) vol *= (double)(ext_hi[a] - ext_lo[a]);
-        double max_keys = std::min(4.0 * count + 4096.0, 1.6e7);
-        edge = std::max(edge, cbrt(vol * s->T / max_keys));
-        long long nc = 1;
-        for (int a = 0; a < 3; a++) {
-            int d = (int)floor((double)(ext_hi[a] - ext_lo[a]) / edge);
-            d = std::max(1, std::min(d, 1024));
-            g.dims[a] = d;
-            g.org[a] = ext_lo[a];
-            g.inv[a] = (float)d / (ext_hi[a] - ext_lo[a]);
-            nc *= d;
-        }
-        g.ncell = (int)nc;
-        g.T = s->T;
-        g.x_min = -INFINITY;
-        g.x_max = INFINITY;
-        const int nkeys = s->T * g.ncell; // key nkeys = "not gridded"
-        if ((size_t)count > s->graph_cap) {
-            CU(cudaStreamSynchronize(s->stream));
-            for (int b = 0; b < 2; b++) {
-                cudaFree(s->gk[b]);
-                cudaFree(s->gv[b]);
-                s->gk[b] = s->gv[b] = nullptr;
-            }
-            cudaFree(s->gpos);
-            s->gpos = nullptr;
-            s->graph_cap = (size_t)count + (size_t)count / 8 + 1024;
-            for (int b = 0; b < 2; b++) {
-                CU(cudaMalloc(&s->gk[b], s->graph_cap * sizeof(uint32_t)));
-                CU(cudaMalloc(&s->gv[b], s->graph_cap * sizeof(uint32_t)));
-            }
-            CU(cudaMalloc(&s->gpos, s->graph_cap * sizeof(float4)));
-        }
-        if ((size_t)nkeys + 2 > s->gstart_cap) {
-            CU(cudaStreamSynchronize(s->stream));
-            cudaFree(s->gstart);
-            s->gstart = nullptr;
-            s->gstart_cap = (size_t)nkeys + 2 + (size_t)nkeys / 4;
-            CU(cudaMalloc(&s->gstart, s->gstart_cap * sizeof(int)));
-        }
-        LAUNCH(s, graph_key_kernel, div_up(count, 256), 256, 0, s->pos[s->cur], first, count, g, s->cell_start, s->ncell,
-               s->base, s->n, use_lo_ghost, use_hi_ghost, s->gk[0], s->gv[0]);
-        int src = 0;
-        if (int rc = radix_sort_pairs(s, s->gk, s->gv, count, (long long)nkeys + 1, &src)) return rc;
-        LAUNCH(s, graph_gather_kernel, div_up(count, 256), 256, 0, s->gv[src], s->pos[s->cur], s->id[s->cur], count, s->gpos);
-        LAUNCH(s, graph_bounds_kernel, div_up(nkeys + 1, 256), 256, 0, s->gk[src], count, s->gstart, nkeys);
-        LAUNCH(s, graph_kernel, div_up(count, CF_GRAPH_THREADS), CF_GRAPH_THREADS,
-               (size_t)3 * 2 * mc * CF_GRAPH_THREADS * sizeof(int), s->gpos, s->gv[src], s->gk[src], s->gstart, count, s->base,
-               s->n, g, dist * dist, mc, s->edges, s->edge_slots, s->edge_cap, s->d_edge_count);
-    }
+    s->last_graph_kernel = P.gkernel;
     if (s->opt_timing) {
         CU(cudaEventRecord(s->ev_g1, s->stream));
         s->graph_timed = true;
     }
+    CU(cudaMemcpyAsync(&s->h_graph_occ, s->d_graph_occ, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->stream));
     CU(cudaMemcpyAsync(&s->n_edges, s->d_edge_count, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
     CU(cudaStreamSynchronize(s->stream));
     CU(cudaGetLastError());
+    if (P.count > 0 && s->n > 0) s->graph_mean_occ = (double)s->h_graph_occ / (double)P.count;
     *n_edges = s->n_edges;
     return CF_OK;
 }
@@ -1333,6 +1460,7 @@ extern "C" int cf_set_option(cf_sim* s, const char* name, double value) {
     std::string k(name);
     if (k == "stencil") s->opt_stencil = (int)value;
     else if (k == "force_kernel") s->opt_force_kernel = (int)value;
+    else if (k == "graph_kernel") s->opt_graph_kernel = (int)value; // 0 auto, 1 thread per particle, 2 warp per particle
     else if (k == "timing") s->opt_timing = (int)value;
     else if (k == "max_cells_per_particle") s->opt_max_cells_per_particle = value;
     else if (k == "cuda_graphs") s->opt_graphs = (int)value;

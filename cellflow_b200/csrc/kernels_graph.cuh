@@ -203,6 +203,105 @@ graph_kernel(const float4* __restrict__ gpos, const uint32_t* __restrict__ gvals
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Dense states: ONE WARP PER PARTICLE.  With hundreds of candidates per particle (the reference's
+// spawn cube, or any clustered state) the thread-per-particle kernel above runs its insertion
+// path on almost every candidate for the whole warp (lanes accept different candidates), and its
+// per-thread serial scan is long.  Here the 32 lanes test 32 consecutive candidates at once
+// (coalesced loads), and the 2*maxConn smallest ids are kept in a list DISTRIBUTED OVER THE LANES
+// (lane r holds the r-th smallest id so far): inserting one accepted candidate is a ballot, a
+// popc and three shuffles, warp-uniform, no shared memory.  Same rule, same edge set.
+// ---------------------------------------------------------------------------------------------
+#define CF_GRAPHW_WARPS 4
+__global__ void __launch_bounds__(CF_GRAPHW_WARPS * 32)
+graph_warp_kernel(const float4* __restrict__ gpos, const uint32_t* __restrict__ gvals, const uint32_t* __restrict__ gkeys,
+                  const int* __restrict__ gstart, int nq, int own_first, int n_own, GraphGrid g, float dist2,
+                  int max_conn, int2* __restrict__ edges, int2* __restrict__ edge_slots, int capacity,
+                  int* __restrict__ edge_count) {
+    const int lane = threadIdx.x & 31;
+    const int q = blockIdx.x * CF_GRAPHW_WARPS + (threadIdx.x >> 5); // warp-uniform
+    if (q >= nq) return;
+    const uint32_t key = gkeys[q];
+    const int my_slot = (int)gvals[q];
+    if (!(key < (uint32_t)g.T * (uint32_t)g.ncell && my_slot >= own_first && my_slot < own_first + n_own)) return;
+    const int K = 2 * max_conn; // <= 32: one list entry per lane
+    const float4 p = gpos[q];
+    const int my_id = __float_as_int(p.w);
+    const int t = (int)(key / (uint32_t)g.ncell);
+    const int cell = (int)(key - (uint32_t)t * (uint32_t)g.ncell);
+    const int cz = cell % g.dims[2], cy = (cell / g.dims[2]) % g.dims[1], cx = cell / (g.dims[2] * g.dims[1]);
+    const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.dims[0] - 1);
+    const int y0 = max(cy - 1, 0), y1 = min(cy + 1, g.dims[1] - 1);
+    const int z0 = max(cz - 1, 0), z1 = min(cz + 1, g.dims[2] - 1);
+    const int tbase = t * g.ncell;
+    // distributed list, sorted by id: lane r < cnt holds the r-th smallest candidate id
+    int l_id = 0x7fffffff, l_q = 0;
+    float l_d2 = 0.f;
+    int cnt = 0, kth = 0x7fffffff; // kth = largest id kept when the list is full
+    for (int x = x0; x <= x1; x++)
+        for (int y = y0; y <= y1; y++) {
+            const int row = tbase + (x * g.dims[1] + y) * g.dims[2];
+            const int j0 = gstart[row + z0], j1 = gstart[row + z1 + 1];
+            for (int c0 = j0; c0 < j1; c0 += 32) {
+                const int j = c0 + lane;
+                float4 o = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+                if (j < j1) o = gpos[j];
+                const int jid = __float_as_int(o.w);
+                const float dx = __fsub_rn(o.x, p.x), dy = __fsub_rn(o.y, p.y), dz = __fsub_rn(o.z, p.z);
+                const float d2 = cf_dist2(dx, dy, dz);
+                unsigned acc = __ballot_sync(0xffffffffu, jid > my_id && d2 < dist2 && jid < kth);
+                while (acc) {
+                    const int src = __ffs(acc) - 1;
+                    acc &= acc - 1;
+                    const int c_id = __shfl_sync(0xffffffffu, jid, src);
+                    if (c_id >= kth) continue; // the list filled up meanwhile (warp-uniform)
+                    const float c_d2 = __shfl_sync(0xffffffffu, d2, src);
+                    const int pos = __popc(__ballot_sync(0xffffffffu, l_id < c_id)); // entries that stay in front
+                    const int u_id = __shfl_up_sync(0xffffffffu, l_id, 1);
+                    const int u_q = __shfl_up_sync(0xffffffffu, l_q, 1);
+                    const float u_d2 = __shfl_up_sync(0xffffffffu, l_d2, 1);
+                    if (lane == pos) l_id = c_id, l_q = c0 + src, l_d2 = c_d2;
+                    else if (lane > pos) l_id = u_id, l_q = u_q, l_d2 = u_d2;
+                    if (lane >= K) l_id = 0x7fffffff; // dropped: the largest id of a full list
+                    cnt = min(cnt + 1, K);
+                    if (cnt == K) kth = __shfl_sync(0xffffffffu, l_id, K - 1);
+                }
+            }
+        }
+    if (cnt == 0) return;
+    // stable sort by d2 (.cu:235-243): rank of entry r = entries with smaller d2, or equal d2 and
+    // smaller list position (the list is in index order, as the reference's scan produces it)
+    int rank = 0;
+    for (int b = 0; b < cnt; b++) {
+        const float bd = __shfl_sync(0xffffffffu, l_d2, b);
+        rank += (bd < l_d2 || (bd == l_d2 && b < lane)) ? 1 : 0;
+    }
+    const int w = min(cnt, max_conn);
+    int base = 0;
+    if (lane == 0) base = atomicAdd(edge_count, w);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (lane < cnt && rank < w) {
+        const int e = base + rank;
+        if (e < capacity) {
+            edges[e] = make_int2(my_id, l_id);
+            edge_slots[e] = make_int2(my_slot, (int)gvals[l_q]);
+        }
+    }
+}
+
+// Sum over keys of (particles of the key)^2: divided by the particle count it is the mean number
+// of same-(type, cell) companions of a particle, which decides between the two graph kernels.
+__global__ void graph_occupancy_kernel(const int* __restrict__ gstart, int nkeys, unsigned long long* __restrict__ sumsq) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long v = 0;
+    if (k < nkeys) {
+        const unsigned long long c = (unsigned long long)(gstart[k + 1] - gstart[k]);
+        v = c * c;
+    }
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(sumsq, v);
+}
+
 // Reference VBO layout (.cu:255-275): per edge 2 vertices x (pos xyz + colour of i's type).
 __global__ void graph_vertices_kernel(const int2* __restrict__ edge_slots, int ne,
                                       const float4* __restrict__ pos4, const float* __restrict__ colors,

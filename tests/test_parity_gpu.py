@@ -202,10 +202,12 @@ def test_cell_assignment_bit_exact():
 
 @pytest.mark.parametrize("mode,n,dist,mc", [("cube", 20000, 200.0, 5), ("uniform", 30000, 500.0, 3),
                                             ("blobs", 20000, 120.0, 16), ("cube", 5000, 200.0, 20)])
-def test_graph_edge_set_bit_exact(mode, n, dist, mc):
+@pytest.mark.parametrize("gkernel", [1, 2])
+def test_graph_edge_set_bit_exact(mode, n, dist, mc, gkernel):
+    """gkernel 1 = thread per particle, 2 = warp per particle (dense states)."""
     p, table, radio = U.config("eater")
     state, counts = U.random_state(n, 6, 21, p.canvas, mode)
-    sim = make_sim(p, table, radio, state, counts)
+    sim = make_sim(p, table, radio, state, counts, graph_kernel=gkernel)
     colors = np.zeros(10, cf.COLOR)
     colors["r"], colors["g"], colors["b"] = np.arange(10) * 0.1, 0.5, 1.0 - np.arange(10) * 0.1
     edges, verts = sim.generateProximityGraph(dist, mc, colors)
@@ -218,6 +220,25 @@ def test_graph_edge_set_bit_exact(mode, n, dist, mc):
     sim.close()
 
 
+def test_graph_dense_cluster_and_ties():
+    """A tight cluster (hundreds of same-type candidates per particle, many of them at exactly the
+    same distance) through both graph kernels and the automatic choice: the edge set is the rule's."""
+    p, table, radio = U.config("eater")
+    state, counts = U.random_state(6000, 6, 33, p.canvas, "cube", cube=300.0)
+    state["pos"] = np.round(state["pos"] / 25.0).astype(np.float32) * 25.0   # lattice: equal distances
+    want = O.graph(state, 200.0, 5, canvas=p.canvas, method="cells")
+    for gk in (1, 2):
+        sim = make_sim(p, table, radio, state, counts, graph_kernel=gk)
+        edges, _ = sim.generateProximityGraph(200.0, 5)
+        assert U.edge_set(edges) == U.edge_set(want), f"graph_kernel={gk}"
+        sim.close()
+    sim = make_sim(p, table, radio, state, counts)   # automatic choice
+    for call in range(2):   # the second call has seen the occupancy of the first
+        edges, _ = sim.generateProximityGraph(200.0, 5)
+        assert U.edge_set(edges) == U.edge_set(want), f"automatic, call {call}"
+    sim.close()
+
+
 def test_graph_after_steps_uses_current_positions():
     p, table, radio = U.config("pulser")
     state, counts = U.random_state(10000, 6, 2, p.canvas, "cube")
@@ -226,6 +247,24 @@ def test_graph_after_steps_uses_current_positions():
     now = sim.getParticleData()
     edges, _ = sim.generateProximityGraph(200.0, 5)
     assert U.edge_set(edges) == U.edge_set(O.graph(now, 200.0, 5, canvas=p.canvas, method="cells"))
+    sim.close()
+
+
+def test_graph_replayed_cuda_graphs_track_the_state():
+    """step + graph, ten times: from the third time on both the step and the graph build replay
+    captured CUDA graphs (two ping-pong parities each); every build must still be the rule applied
+    to the positions of that moment, and a repeated build without a step in between as well."""
+    p, table, radio = U.config("pulser")
+    state, counts = U.random_state(6000, 6, 4, p.canvas, "cube")
+    sim = make_sim(p, table, radio, state, counts)
+    for it in range(10):
+        sim.simulate()
+        edges, _ = sim.generateProximityGraph(200.0, 5)
+        now = sim.getParticleData()
+        assert U.edge_set(edges) == U.edge_set(O.graph(now, 200.0, 5, canvas=p.canvas, method="cells")), it
+        if it % 4 == 3:
+            again, _ = sim.generateProximityGraph(200.0, 5)
+            assert U.edge_set(again) == U.edge_set(edges)
     sim.close()
 
 
