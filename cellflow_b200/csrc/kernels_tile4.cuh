@@ -223,16 +223,38 @@ force_tile4_kernel(const float4* __restrict__ pos4, const int* __restrict__ cell
     const unsigned stage_addr = (unsigned)__cvta_generic_to_shared(&sm.x[warp][0][0]); // + buf*256 + 4*slot
     constexpr unsigned STRIDE = T4_WARPS * 2 * T4_JC * 4;
 
+    // Tail: the tiles of the last, partly filled round (ntiles mod warps-of-the-grid) are handed out
+    // as 2 or 4 sub-tiles of 2 or 1 layers when that shortens the round: a sub-tile costs its share
+    // plus ~8 % per halving (the j stream is staged for fewer layers).
+    const int nwarps = (int)gridDim.x * T4_WARPS;
+    const int tail = ntiles % nwarps, full = ntiles - tail;
+    int split = 1;
+    if (tail > 0) {
+        const float c1 = 1.0f;
+        const float c2 = 0.5f * 1.08f * (float)((2 * tail + nwarps - 1) / nwarps);
+        const float c4 = 0.25f * 1.22f * (float)((4 * tail + nwarps - 1) / nwarps);
+        split = (c2 < c1 && c2 <= c4) ? 2 : ((c4 < c1 && c4 < c2) ? 4 : 1);
+    }
+    const int nvirtual = full + tail * split;
+
     for (;;) {
         int tile = 0;
         if (lane == 0) tile = atomicAdd(&ctrl[1], 1);
         tile = __shfl_sync(0xffffffffu, tile, 0);
-        if (tile >= ntiles) break;
+        if (tile >= nvirtual) break;
+        int first_layer = 0, max_i = TK_TI;
+        if (tile >= full) { // a sub-tile of a tail tile
+            const int v = tile - full;
+            tile = full + v / split;
+            max_i = TK_TI / split;
+            first_layer = (v % split) * (TK_IPT / split);
+        }
         const int2 tl = tiles[tile];
         const int cell = tl.x;
         const int cz = cell % nz, cy = (cell / nz) % ny, cx = cell / (nz * ny);
-        const int i_begin = cell_start[cell] + tl.y * TK_TI;
-        const int ni = min(cell_start[cell + 1] - i_begin, TK_TI);
+        const int i_begin = cell_start[cell] + tl.y * TK_TI + 32 * first_layer;
+        const int ni = min(cell_start[cell + 1] - i_begin, max_i);
+        if (ni <= 0) continue; // this part of the tile holds no particle
 
         // ---- neighbour runs: lane r < 18 holds run r = (row r/2 of the 3x3 (x,y) rows, z segment r%2)
         int r_code = 0; // minimum-image shift of the run, 2 bits per axis: 1 = -W, 2 = +W
