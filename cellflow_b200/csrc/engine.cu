@@ -168,7 +168,6 @@ struct cf_sim {
     int opt_graphs = 1;
 
     // options
-    int opt_stencil = 0;     // reserved (0 = automatic)
     int opt_force_kernel = 0; // 0 auto, 1 per-particle, 2 tile (generation 3), 3 tile (generation 4)
     int opt_timing = 0;
     double opt_max_cells_per_particle = 16.0; // fine grids pay off for clustered states (cells are cheap)
@@ -1458,8 +1457,7 @@ extern "C" int cf_apply_preset(cf_sim* s, const cf_preset* pr) {
 extern "C" int cf_set_option(cf_sim* s, const char* name, double value) {
     ARG(s && name);
     std::string k(name);
-    if (k == "stencil") s->opt_stencil = (int)value;
-    else if (k == "force_kernel") s->opt_force_kernel = (int)value;
+    if (k == "force_kernel") s->opt_force_kernel = (int)value;
     else if (k == "graph_kernel") s->opt_graph_kernel = (int)value; // 0 auto, 1 thread per particle, 2 warp per particle
     else if (k == "timing") s->opt_timing = (int)value;
     else if (k == "max_cells_per_particle") s->opt_max_cells_per_particle = value;

@@ -253,7 +253,17 @@ int cf_stats_reset(cf_sim* sim);
 /* Sorted-order views for the cell-assignment parity tests: sort key (= cell * 64 + Morton code of the 4x4x4 sub-cell) and
  * original id per slot. */
 int cf_download_cell_keys(cf_sim* sim, uint32_t* keys, int32_t* ids, int capacity, int* count);
-/* Tuning knobs (0 = automatic): stencil half-width m (cell edge = R_max/m rounded to the grid). */
+/* Tuning knobs; every one defaults to the automatic choice and none changes a result beyond the
+ * summation order of the force terms:
+ *   "force_kernel"   0 auto | 1 one thread per particle | 2 tile kernel, generation 3 |
+ *                    3 tile kernel, generation 4 (box prefilter, type-sorted j stream)
+ *   "graph_kernel"   0 auto | 1 one thread per particle | 2 one warp per particle (dense states)
+ *   "cuda_graphs"    1 (default): single-GPU step and graph build replay captured CUDA graphs
+ *   "timing"         0 off | 1 events between the phases of a step | 2 events around whole steps
+ *   "max_cells_per_particle"   upper bound of grid cells per particle (default 16)
+ *   "global_particle_count", "halo_slack", "migrant_slack", "halo_capacity", "migrant_capacity"
+ *                    slab-mode message sizing (the two capacities before cf_comm_init)
+ * Unknown names return CF_ERR_ARG. */
 int cf_set_option(cf_sim* sim, const char* name, double value);
 /* Measurement helpers for bench.py (not on the simulation path): live FP32 FMA peak of the
  * device in TFLOP/s (roofline denominator of the pair-force kernel) and an L2 flush that
