@@ -239,11 +239,13 @@ def run_ours(args):
     _lib.check(L.cf_bench_fp32_peak(C.c_int(dev), C.byref(tf), C.byref(mhz)))
     achieved = 37.0 * accepted / (force_ms * 1e-3) * 1e-12 if force_ms > 0 else 0.0
     traffic = None  # dram bytes of the force kernel per launch, from the committed ncu capture
+    pipes = None    # pipe utilisation of the same capture (what the FP32-bound kernel actually loads)
     try:
         with open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")) as f:
             t = json.load(f).get(args.workload)
         if t:
             traffic = t["dram_bytes_read"] + t["dram_bytes_write"]
+            pipes = t.get("pipes_pct_of_peak_sustained_active")
     except Exception:
         pass
     peaks, peak_src = measured_peaks()
@@ -253,6 +255,7 @@ def run_ours(args):
         "unit": "TFLOP/s", "frac": round(achieved / tf.value, 4) if tf.value else None, "traffic": traffic,
         "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full)",
         "algorithmic_bytes_per_launch": 32 * n,  # read pos4 16 B + write frc4 16 B per particle
+        "ncu_pipes_pct": pipes,  # from the committed ncu --set full capture of this workload (profiles/)
         "peak_source": "FFMA microbenchmark measured in this run (no FP32 figure in MEASURED_PEAKS.json)",
         "flops_per_accepted_pair": 37, "accepted_pairs_per_step": accepted, "tested_pairs_per_step": tested,
         "pair_tests_per_s": round(tested / (force_ms * 1e-3), 1) if force_ms > 0 else None,
