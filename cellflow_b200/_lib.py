@@ -103,7 +103,8 @@ class Stats(C.Structure):
         ("ms_integrate", C.c_double), ("ms_exchange", C.c_double), ("ms_graph", C.c_double),
         ("steps", C.c_int64), ("launches", C.c_int64), ("accepted_pairs", C.c_int64),
         ("tested_pairs", C.c_int64), ("grid", C.c_int32 * 3), ("stencil", C.c_int32),
-        ("n_owned", C.c_int32), ("n_ghost", C.c_int32), ("force_kernel", C.c_int32), ("reserved", C.c_int32),
+        ("n_owned", C.c_int32), ("n_ghost", C.c_int32), ("force_kernel", C.c_int32), ("graph_kernel", C.c_int32),
+        ("ms_graph_total", C.c_double), ("graph_builds", C.c_int64),
     ]
 
 

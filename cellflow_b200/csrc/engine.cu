@@ -177,7 +177,8 @@ struct cf_sim {
     size_t ev_used = 0;
     cudaEvent_t ev_g0 = nullptr, ev_g1 = nullptr;
     bool graph_timed = false;
-    double ms_sort = 0, ms_force = 0, ms_integrate = 0, ms_total = 0, ms_graph = 0;
+    double ms_sort = 0, ms_force = 0, ms_integrate = 0, ms_total = 0, ms_graph = 0, ms_graph_total = 0;
+    long long graph_builds = 0;
     long long stat_steps = 0;
     long long launches = 0;
     long long tested_pairs = 0;
@@ -1174,6 +1175,19 @@ extern "C" int cf_step_host(cf_sim* s, const cf_params* p, const cf_particle* in
 // ---------------------------------------------------------------------------------------------
 // proximity graph
 // ---------------------------------------------------------------------------------------------
+// The graph events of the previous build have completed (every build ends with a stream
+// synchronisation): fold them into the totals before the pair of events is reused.
+static void fold_graph_timing(cf_sim* s) {
+    if (!s->graph_timed) return;
+    float g = 0;
+    if (cudaEventElapsedTime(&g, s->ev_g0, s->ev_g1) == cudaSuccess) {
+        s->ms_graph = g;
+        s->ms_graph_total += g;
+        s->graph_builds++;
+    }
+    s->graph_timed = false;
+}
+
 // Everything cf_build_graph launches depends on this plan (plus the buffers and the step constants).
 struct GraphPlan {
     int first, count;            // slots [first, first + count) are keyed
@@ -1371,6 +1385,7 @@ extern "C" int cf_build_graph(cf_sim* s, float dist, int max_conn, int* n_edges)
         CU(cudaMalloc(&s->edge_slots, sizeof(int2) * (size_t)need));
         s->edge_cap = (int)need;
     }
+    fold_graph_timing(s);
     if (s->opt_timing) CU(cudaEventRecord(s->ev_g0, s->stream));
     GraphPlan P;
     if (s->slab) {
@@ -1478,6 +1493,8 @@ extern "C" int cf_stats_reset(cf_sim* s) {
     CU(cudaStreamSynchronize(s->stream));
     s->ev_used = 0;
     s->ms_sort = s->ms_force = s->ms_integrate = s->ms_total = s->ms_graph = s->ms_exchange = 0;
+    s->ms_graph_total = 0;
+    s->graph_builds = 0;
     s->stat_steps = 0;
     s->launches = 0;
     s->graph_timed = false;
@@ -1505,12 +1522,7 @@ extern "C" int cf_get_stats(cf_sim* s, cf_stats* st) {
         s->stat_steps++;
     }
     s->ev_used = 0;
-    if (s->graph_timed) {
-        float g = 0;
-        cudaEventElapsedTime(&g, s->ev_g0, s->ev_g1);
-        s->ms_graph = g;
-        s->graph_timed = false;
-    }
+    fold_graph_timing(s);
     memset(st, 0, sizeof(*st));
     st->ms_total = s->ms_total;
     st->ms_sort = s->ms_sort;
@@ -1525,7 +1537,9 @@ extern "C" int cf_get_stats(cf_sim* s, cf_stats* st) {
     st->n_owned = s->n;
     st->n_ghost = 0;
     st->force_kernel = s->last_force_kernel;
-    st->reserved = 0;
+    st->graph_kernel = s->last_graph_kernel;
+    st->ms_graph_total = s->ms_graph_total;
+    st->graph_builds = s->graph_builds;
     if (s->slab) {
         int g[2] = {0, 0};
         CU(cudaMemcpy(g, s->d_slab_counts + 4, 2 * sizeof(int), cudaMemcpyDeviceToHost));

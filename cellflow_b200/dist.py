@@ -206,19 +206,17 @@ def bench_multi(args, workloads, workload_setup):
     sim.statsReset()
     barrier()
     torch.cuda.synchronize()
-    graph_ms = 0.0
     with ClockSampler(local) as clocks:
         t0 = time.perf_counter()
         for _ in range(args.steps):
             _lib.check(L.cf_bench_flush_l2(C.c_int(local), C.c_size_t(256 << 20)))
             one_step()
             sim.sync()
-            if graph:
-                graph_ms += sim.stats().ms_graph
         torch.cuda.synchronize()
         barrier()
         wall = time.perf_counter() - t0
         st = sim.stats()
+        graph_ms = st.ms_graph_total  # accumulated inside the library: no per-step stats call (it synchronises)
     my_ms = st.ms_total / max(st.steps, 1) + graph_ms / args.steps
     step_ms = all_reduce_max(my_ms)
     owned = all_reduce_sum(float(st.n_owned))

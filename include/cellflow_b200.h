@@ -126,7 +126,9 @@ typedef struct cf_stats {
     int32_t stencil;       /* half-width m of the (2m+1)^3 neighbour stencil */
     int32_t n_owned, n_ghost;
     int32_t force_kernel;  /* pair-force kernel of the last step: 1 per-particle, 2 tile gen. 3, 3 tile gen. 4 */
-    int32_t reserved;
+    int32_t graph_kernel;  /* kernel of the last cf_build_graph: 1 thread per particle, 2 warp per particle */
+    double ms_graph_total; /* all cf_build_graph calls since cf_stats_reset (timing != 0) */
+    int64_t graph_builds;  /* ... and how many they were */
 } cf_stats;
 
 typedef struct cf_sim cf_sim;
