@@ -230,44 +230,68 @@ graph_warp_kernel(const float4* __restrict__ gpos, const uint32_t* __restrict__ 
     const int t = (int)(key / (uint32_t)g.ncell);
     const int cell = (int)(key - (uint32_t)t * (uint32_t)g.ncell);
     const int cz = cell % g.dims[2], cy = (cell / g.dims[2]) % g.dims[1], cx = cell / (g.dims[2] * g.dims[1]);
-    const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.dims[0] - 1);
-    const int y0 = max(cy - 1, 0), y1 = min(cy + 1, g.dims[1] - 1);
     const int z0 = max(cz - 1, 0), z1 = min(cz + 1, g.dims[2] - 1);
     const int tbase = t * g.ncell;
+    // the <= 9 candidate ranges (one per (x, y) row; z-adjacent cells of a type are contiguous):
+    // lane r < 9 fetches the bounds of row r, so the 18 loads are two instructions
+    int r_j0 = 0, r_j1 = 0;
+    if (lane < 9) {
+        const int x = cx + lane / 3 - 1, y = cy + lane % 3 - 1;
+        if (x >= 0 && x < g.dims[0] && y >= 0 && y < g.dims[1]) {
+            const int row = tbase + (x * g.dims[1] + y) * g.dims[2];
+            r_j0 = gstart[row + z0];
+            r_j1 = gstart[row + z1 + 1];
+        }
+    }
     // distributed list, sorted by id: lane r < cnt holds the r-th smallest candidate id
     int l_id = 0x7fffffff, l_q = 0;
     float l_d2 = 0.f;
     int cnt = 0, kth = 0x7fffffff; // kth = largest id kept when the list is full
-    for (int x = x0; x <= x1; x++)
-        for (int y = y0; y <= y1; y++) {
-            const int row = tbase + (x * g.dims[1] + y) * g.dims[2];
-            const int j0 = gstart[row + z0], j1 = gstart[row + z1 + 1];
-            for (int c0 = j0; c0 < j1; c0 += 32) {
-                const int j = c0 + lane;
-                float4 o = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
-                if (j < j1) o = gpos[j];
-                const int jid = __float_as_int(o.w);
-                const float dx = __fsub_rn(o.x, p.x), dy = __fsub_rn(o.y, p.y), dz = __fsub_rn(o.z, p.z);
-                const float d2 = cf_dist2(dx, dy, dz);
-                unsigned acc = __ballot_sync(0xffffffffu, jid > my_id && d2 < dist2 && jid < kth);
-                while (acc) {
-                    const int src = __ffs(acc) - 1;
-                    acc &= acc - 1;
-                    const int c_id = __shfl_sync(0xffffffffu, jid, src);
-                    if (c_id >= kth) continue; // the list filled up meanwhile (warp-uniform)
-                    const float c_d2 = __shfl_sync(0xffffffffu, d2, src);
-                    const int pos = __popc(__ballot_sync(0xffffffffu, l_id < c_id)); // entries that stay in front
-                    const int u_id = __shfl_up_sync(0xffffffffu, l_id, 1);
-                    const int u_q = __shfl_up_sync(0xffffffffu, l_q, 1);
-                    const float u_d2 = __shfl_up_sync(0xffffffffu, l_d2, 1);
-                    if (lane == pos) l_id = c_id, l_q = c0 + src, l_d2 = c_d2;
-                    else if (lane > pos) l_id = u_id, l_q = u_q, l_d2 = u_d2;
-                    if (lane >= K) l_id = 0x7fffffff; // dropped: the largest id of a full list
-                    cnt = min(cnt + 1, K);
-                    if (cnt == K) kth = __shfl_sync(0xffffffffu, l_id, K - 1);
-                }
-            }
+    // chunks of 32 candidates over all rows; the next chunk is loaded before the current one is
+    // processed (the kernel is bound by the latency of these loads and of the insertions)
+    int row = -1, c0 = 0, end = 0;
+    bool have;
+#define GW_ADVANCE()                                       \
+    do {                                                   \
+        c0 += 32;                                          \
+        have = true;                                       \
+        while (c0 >= end) {                                \
+            if (++row >= 9) { have = false; break; }       \
+            c0 = __shfl_sync(0xffffffffu, r_j0, row);      \
+            end = __shfl_sync(0xffffffffu, r_j1, row);     \
+        }                                                  \
+    } while (0)
+    GW_ADVANCE();
+    float4 nxt = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+    if (have && c0 + lane < end) nxt = gpos[c0 + lane];
+    while (have) {
+        const float4 o = nxt;
+        const int base = c0;
+        GW_ADVANCE();
+        nxt = make_float4(0.f, 0.f, 0.f, __int_as_float(-1)); // id -1 is never a candidate
+        if (have && c0 + lane < end) nxt = gpos[c0 + lane];
+        const int jid = __float_as_int(o.w);
+        const float dx = __fsub_rn(o.x, p.x), dy = __fsub_rn(o.y, p.y), dz = __fsub_rn(o.z, p.z);
+        const float d2 = cf_dist2(dx, dy, dz);
+        unsigned acc = __ballot_sync(0xffffffffu, jid > my_id && d2 < dist2 && jid < kth);
+        while (acc) {
+            const int src = __ffs(acc) - 1;
+            acc &= acc - 1;
+            const int c_id = __shfl_sync(0xffffffffu, jid, src);
+            if (c_id >= kth) continue; // the list filled up meanwhile (warp-uniform)
+            const float c_d2 = __shfl_sync(0xffffffffu, d2, src);
+            const int pos = __popc(__ballot_sync(0xffffffffu, l_id < c_id)); // entries that stay in front
+            const int u_id = __shfl_up_sync(0xffffffffu, l_id, 1);
+            const int u_q = __shfl_up_sync(0xffffffffu, l_q, 1);
+            const float u_d2 = __shfl_up_sync(0xffffffffu, l_d2, 1);
+            if (lane == pos) l_id = c_id, l_q = base + src, l_d2 = c_d2;
+            else if (lane > pos) l_id = u_id, l_q = u_q, l_d2 = u_d2;
+            if (lane >= K) l_id = 0x7fffffff; // dropped: the largest id of a full list
+            cnt = min(cnt + 1, K);
+            if (cnt == K) kth = __shfl_sync(0xffffffffu, l_id, K - 1);
         }
+    }
+#undef GW_ADVANCE
     if (cnt == 0) return;
     // stable sort by d2 (.cu:235-243): rank of entry r = entries with smaller d2, or equal d2 and
     // smaller list position (the list is in index order, as the reference's scan produces it)
