@@ -160,7 +160,10 @@ __device__ __forceinline__ void t4_chunk(unsigned sbase, const unsigned (&live)[
         const u64 za = tk_pack(Z.x, Z.y), zb = tk_pack(Z.z, Z.w);
 #pragma unroll
         for (int k = 0; k < TK_IPT; k++) {
-            if (!(live[k] & bit)) continue; // warp-uniform
+            // MODE 0: layers whose box is not near skip the exact test (warp-uniform branch).  MODE 1 tests
+            // every layer of a live quad: there the extra branch costs more than the tests it saves
+            // (measured: eater 4.89 -> 4.76 ms without it, pulser 1.96 -> 2.30 ms without it)
+            if (MODE == 0 && !(live[k] & bit)) continue;
             float4 cs = make_float4(c2u, pau, pbu, cutu);
             if (MODE == 1) cs = cst[k * 32];
             const u64 px = tk_pack(npx[k], npx[k]), py = tk_pack(npy[k], npy[k]), pz = tk_pack(npz[k], npz[k]);
