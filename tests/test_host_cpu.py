@@ -41,6 +41,30 @@ def test_struct_layouts_match_header():
         assert getattr(p, f) == getattr(d, f), f
 
 
+def test_ctypes_mirror_matches_the_compiled_header(tmp_path):
+    """The header is the contract: gcc compiles it as plain C and prints size and field offsets of
+    the structs that cross the boundary by pointer; the ctypes mirror must agree byte for byte."""
+    import subprocess
+
+    fields = {"cf_stats": [f for f, _ in _lib.Stats._fields_], "cf_params": [f for f, _ in cf.Params._fields_]}
+    prog = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', 'int main(void) {']
+    for st, fs in fields.items():
+        prog.append(f'  printf("{st} %zu", sizeof({st}));')
+        for f in fs:
+            prog.append(f'  printf(" %zu", offsetof({st}, {f}));')
+        prog.append('  printf("\\n");')
+    prog += ['  printf("cf_particle %zu\\n", sizeof(cf_particle));', '  return 0;', '}']
+    src = tmp_path / "abi.c"
+    src.write_text("\n".join(prog))
+    exe = tmp_path / "abi"
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-o", str(exe), str(src)])
+    out = dict((l.split()[0], [int(x) for x in l.split()[1:]]) for l in subprocess.check_output([str(exe)], text=True).splitlines())
+    for st, cls in (("cf_stats", _lib.Stats), ("cf_params", cf.Params)):
+        assert out[st][0] == C.sizeof(cls), st
+        assert out[st][1:] == [getattr(cls, f).offset for f, _ in cls._fields_], st
+    assert out["cf_particle"] == [44]
+
+
 @pytest.mark.parametrize("name", ["settings", "littlecells", "eater", "pulser"])
 def test_load_preset_matches_json(name):
     pr = cf.load_preset(os.path.join(U.PRESETS, name + ".json"))
