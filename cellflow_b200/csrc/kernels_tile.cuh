@@ -1,4 +1,7 @@
-// kernels_tile.cuh — tiled pair-force kernel for dense cells (the FP32-bound hot kernel).
+// kernels_tile.cuh — tiled pair-force kernel for dense cells, GENERATION 3 (kept selectable with
+// cf_set_option("force_kernel", 2) and used for per-type radii with short sub-runs; the default dense
+// kernel is generation 4, kernels_tile4.cuh, which reuses the packed-math helpers and the tile list
+// builder defined here).
 //
 // Work decomposition
 //   tile  = up to TK_TI (128) particles of ONE cell ("i" side), owned by one WARP: every lane

@@ -4,14 +4,15 @@
 // 4 register-resident layers of 32; the 27 neighbour cells are streamed as <= 18 contiguous runs
 // through a warp-private double buffer, 128 j per chunk; one warp vote per (layer, quad of 4 j)
 // gates the force terms), with what the round-1 ncu captures asked for
-// (profiles/r01_force_kernel_history.md, profiles/r02_force_kernel.md):
+// (profiles/r01_force_kernel_history.md):
 //
 //   * BOX PREFILTER.  The exact test of a (layer, quad) block costs 12 packed FP32 instructions
 //     = 24 FMA-pipe cycles per SM sub-partition, and 50-70% of the blocks are dead.  A chunk is
 //     128 staged j, one quad of 4 consecutive j per lane: each lane takes the bounding box of its
 //     own quad (no shuffles) and tests it against the bounding box of each layer's 32 i (4
-//     ballots per chunk); only combinations whose boxes come within the cut-off run the exact
-//     test, and the quad loop walks the set bits only, so dead quads cost nothing.
+//     ballots per chunk).  The quad loop walks the quads with a live layer only (dead quads cost
+//     nothing); uniform radii (MODE 0) also skip the layers of a live quad whose own box is far,
+//     per-type radii (MODE 1) test all of them (the extra branch cost more than it saved there).
 //   * TYPE-HOMOGENEOUS j RUNS for per-type radii (MODE 1).  The j stream comes from a second
 //     copy of the positions sorted by (xy row, type, z cell, Morton): inside a sub-run every j
 //     has the same type, so cut2 / force value / 1/Reff of a pair depend on the lane only and
@@ -23,7 +24,9 @@
 //   * 96 REGISTERS, 5 CTAs per SM: scalar force accumulators, layer boxes in shared memory, the
 //     next chunk prefetched into L1 by a hint instead of into registers (and across run
 //     boundaries); one code path for every tile occupancy (empty layers have empty boxes and
-//     are never live).
+//     positions at 1e30, so they are never live).
+//   * TAIL.  The tiles of the last, partly filled round of the persistent grid are handed out as
+//     sub-tiles of 2 or 1 layers when that shortens the round.
 //
 // Exactness is unchanged: displacement = (jx + (-px)) [+ s], s in {-W, 0, +W} per run (exact,
 // see kernels_tile.cuh), d2 = fma(dz,dz, fma(dx,dx, dy*dy)), accept <=> d2 < cut2[ti][tj].
