@@ -120,6 +120,15 @@ struct cf_sim {
     int2* d_tiles = nullptr;
     size_t tiles_cap = 0;
     int* d_tile_ctrl = nullptr;
+    // particle-weighted cell occupancy (sum n_c^2) of the last completed step: device scalar and a
+    // pinned host copy that every step refreshes asynchronously (read without synchronising)
+    unsigned long long* d_cell_occ = nullptr;
+    unsigned long long* h_cell_occ = nullptr;
+    int planned_force_kernel = 1; // choice for the step being enqueued (part of the graph signature)
+    // the occupancy the choice uses: taken over from h_cell_occ only where the API synchronises anyway
+    // (cf_sync, cf_build_graph, cf_step_host), so the choice is a function of the call sequence, not of timing
+    double policy_occ = 0.0;
+    int occ_stride = 1; // the statistic samples every occ_stride-th cell
     float* d_half = nullptr;      // per-type conservative half radius (non-uniform radii)
     // generation-4 tile kernel, per-type radii: j copy sorted by (xy row, type, z cell, Morton)
     uint32_t* hk[2] = {nullptr, nullptr};
@@ -588,6 +597,10 @@ extern "C" int cf_create(int particle_count, int num_types, int device, cf_sim**
     if (rc == 0 && cudaMalloc(&s->d_edge_count, sizeof(int)) != cudaSuccess) rc = fail(CF_ERR_CUDA, "cudaMalloc");
     if (rc == 0 && cudaMalloc(&s->d_graph_occ, sizeof(unsigned long long)) != cudaSuccess) rc = fail(CF_ERR_CUDA, "cudaMalloc");
     if (rc == 0 && cudaMalloc(&s->d_tile_ctrl, 2 * sizeof(int)) != cudaSuccess) rc = fail(CF_ERR_CUDA, "cudaMalloc");
+    if (rc == 0 && cudaMalloc(&s->d_cell_occ, 2 * sizeof(unsigned long long)) != cudaSuccess) rc = fail(CF_ERR_CUDA, "cudaMalloc");
+    if (rc == 0 && cudaMemset(s->d_cell_occ, 0, 2 * sizeof(unsigned long long)) != cudaSuccess) rc = fail(CF_ERR_CUDA, "cudaMemset");
+    if (rc == 0 && cudaMallocHost(&s->h_cell_occ, sizeof(unsigned long long)) != cudaSuccess) rc = fail(CF_ERR_CUDA, "cudaMallocHost");
+    if (rc == 0) *s->h_cell_occ = 0;
     if (rc == 0 && cudaMalloc(&s->d_half, CF_T_MAX * sizeof(float)) != cudaSuccess) rc = fail(CF_ERR_CUDA, "cudaMalloc");
     if (rc == 0) {
         cudaDeviceProp prop;
@@ -634,6 +647,8 @@ extern "C" int cf_destroy(cf_sim* s) {
     cudaFree(s->gpos);
     cudaFree(s->gstart);
     cudaFree(s->d_tile_ctrl);
+    cudaFree(s->d_cell_occ);
+    if (s->h_cell_occ) cudaFreeHost(s->h_cell_occ);
     cudaFree(s->d_half);
     for (int b = 0; b < 2; b++) {
         cudaFree(s->hk[b]);
@@ -973,23 +988,44 @@ static int build_homog_copy(cf_sim* s) {
     return 0;
 }
 
-static int launch_force(cf_sim* s) {
-    int n = s->n;
-    const float4* pos = s->pos[s->cur];
+// Which pair-force kernel the next step uses (1 per-particle, 2 tile generation 3, 3 tile generation 4).
+static int choose_force_kernel(const cf_sim* s) {
     int kernel = s->opt_force_kernel;
     const int global_nx = s->slab ? s->nxl * s->world : s->sc.dims[0];
     // the tile kernels decide the minimum-image wrap per neighbour cell: >= 4 cells per periodic axis
     const bool wrap_ok = s->sc.dims[1] >= 4 && s->sc.dims[2] >= 4 && global_nx >= 4;
     const bool v3_ok = wrap_ok && (s->sc.uniform_radius || s->half_bound_ok);
-    const bool tile_ok = wrap_ok && tile_kernel_applicable(s->sc, n, s->ncell);
+    // particles per cell as a particle sees it: the uniform estimate, or the measured sum n_c^2 / n of
+    // a previous step when that is larger (clustered states)
+    const double n = (double)std::max(s->n, 1);
+    double occ = n / (double)std::max(s->ncell, 1);
+    occ = std::max(occ, s->policy_occ);
+    const bool tile_ok = wrap_ok && tile_kernel_applicable(occ);
     if (kernel == 0) {
         // generation 4 streams one sub-run per (neighbour run, type) when the radii differ per type:
-        // it needs sub-runs long enough to fill its 64-particle chunks
-        const double subrun = 3.0 * (double)n / (double)std::max(s->ncell, 1) / (s->sc.uniform_radius ? 1.0 : (double)s->T);
+        // it needs sub-runs long enough to fill its chunks
+        const double subrun = 3.0 * occ / (s->sc.uniform_radius ? 1.0 : (double)s->T);
         kernel = !tile_ok ? 1 : (subrun >= 40.0 ? 3 : (v3_ok ? 2 : 1));
     }
     if (kernel == 3 && !wrap_ok) kernel = 1;
     if (kernel == 2 && !v3_ok) kernel = 1;
+    return kernel;
+}
+
+// Call after a stream synchronisation: the statistic of the last completed step becomes the policy input.
+static void refresh_policy(cf_sim* s) {
+    if (s->h_cell_occ && s->n > 0) s->policy_occ = (double)s->occ_stride * (double)*s->h_cell_occ / (double)s->n;
+}
+
+static int launch_force(cf_sim* s) {
+    int n = s->n;
+    const float4* pos = s->pos[s->cur];
+    const int kernel = s->planned_force_kernel;
+    // refresh the occupancy statistic for the choice of a later step (one small launch, no synchronisation)
+    const int occ_stride = s->ncell > (1 << 16) ? 8 : 1;
+    s->occ_stride = occ_stride;
+    LAUNCH(s, cell_occupancy_kernel, div_up(div_up(s->ncell, occ_stride), 256), 256, 0, s->cell_start, s->ncell, occ_stride,
+           s->d_cell_occ, s->h_cell_occ);
     s->last_force_kernel = kernel;
     if (kernel == 2 || kernel == 3) {
         size_t need = (size_t)s->ncell + (size_t)n / TK_TI + 2;
@@ -1058,7 +1094,8 @@ static std::vector<char> step_signature(const cf_sim* s) {
                           s->d_tables, s->d_half, s->hk[0], s->hk[1], s->hv[0], s->hv[1], s->h_cell_of, s->h_pos,
                           s->h_comp, s->h_start};
     put(ptrs, sizeof(ptrs));
-    int ints[] = {s->n, s->ncell, s->cur, s->opt_force_kernel, s->sorted_valid ? 1 : 0, s->half_bound_ok ? 1 : 0};
+    int ints[] = {s->n, s->ncell, s->cur, s->opt_force_kernel, s->sorted_valid ? 1 : 0, s->half_bound_ok ? 1 : 0,
+                  s->planned_force_kernel};
     put(ints, sizeof(ints));
     return sig;
 }
@@ -1147,6 +1184,7 @@ extern "C" int cf_step(cf_sim* s, const cf_params* p, int n_steps) {
     const bool graphs = s->opt_graphs && !s->slab && s->opt_timing != 1 && s->n > 0;
     for (int it = 0; it < n_steps; it++) {
         StepEvents* ev = next_events(s);
+        s->planned_force_kernel = choose_force_kernel(s);
         if (int rc = graphs ? step_graphed(s, ev) : step_direct(s, ev)) return rc;
     }
     CU(cudaGetLastError());
@@ -1157,6 +1195,7 @@ extern "C" int cf_sync(cf_sim* s) {
     ARG(s);
     if (int rc = set_device(s)) return rc;
     CU(cudaStreamSynchronize(s->stream));
+    refresh_policy(s);
     return CF_OK;
 }
 
@@ -1172,6 +1211,7 @@ extern "C" int cf_step_host(cf_sim* s, const cf_params* p, const cf_particle* in
     if (counts_out)
         CU(cudaMemcpyAsync(counts_out, s->d_counts, sizeof(int) * (size_t)count, cudaMemcpyDeviceToHost, s->stream));
     CU(cudaStreamSynchronize(s->stream));
+    refresh_policy(s);
     return CF_OK;
 }
 
@@ -1412,6 +1452,7 @@ extern "C" int cf_build_graph(cf_sim* s, float dist, int max_conn, int* n_edges)
     CU(cudaStreamSynchronize(s->stream));
     CU(cudaGetLastError());
     if (P.count > 0 && s->n > 0) s->graph_mean_occ = (double)s->h_graph_occ / (double)P.count;
+    refresh_policy(s);
     *n_edges = s->n_edges;
     return CF_OK;
 }

@@ -417,9 +417,41 @@ force_tile_kernel(const float4* __restrict__ pos4, const int* __restrict__ cell_
     }
 }
 
-// The tile kernel decides the minimum-image wrap per neighbour cell, which is only equivalent to
-// the reference's per-pair test when every periodic axis has at least 4 cells; it pays off when
-// cells hold enough particles to fill warps.
-static inline bool tile_kernel_applicable(const StepConst&, int n, int ncell) {
-    return (double)n / (double)ncell >= 48.0;
+// The tile kernels decide the minimum-image wrap per neighbour cell, which is only equivalent to
+// the reference's per-pair test when every periodic axis has at least 4 cells; they pay off when
+// the cells that hold the particles hold enough of them to fill warps.  `occupancy` is the number
+// of particles a particle shares its cell with, averaged over PARTICLES (sum n_c^2 / n): for a
+// uniform state that is n / ncell, for a clustered one it is what matters (most cells are empty,
+// most particles sit in full ones).
+static inline bool tile_kernel_applicable(double occupancy) { return occupancy >= 48.0; }
+
+// sum over every `stride`-th cell of (particles in the cell)^2 (the host scales by `stride`: clusters
+// span hundreds of cells, so a strided sample estimates the sum well and costs 1/stride on the
+// huge, mostly empty grids of sparse states).  One launch, no memset, no copy: acc[0] accumulates,
+// acc[1] is a ticket; the block that takes the last ticket publishes the total to `host_out`
+// (pinned, mapped host memory) and resets both for the next step.
+__global__ void cell_occupancy_kernel(const int* __restrict__ cell_start, int ncell, int stride,
+                                      unsigned long long* __restrict__ acc, unsigned long long* host_out) {
+    const long long c = (long long)(blockIdx.x * blockDim.x + threadIdx.x) * stride;
+    unsigned long long v = 0;
+    if (c < ncell) {
+        const unsigned long long k = (unsigned long long)(cell_start[c + 1] - cell_start[c]);
+        v = k * k;
+    }
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0 && v) {
+        atomicAdd(&acc[0], v);
+        __threadfence(); // the contribution is visible before this block's ticket is taken
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned long long ticket = atomicAdd(&acc[1], 1ull);
+        if (ticket == (unsigned long long)gridDim.x - 1ull) { // every other block has contributed
+            __threadfence();
+            const unsigned long long total = atomicExch(&acc[0], 0ull);
+            acc[1] = 0ull;
+            *reinterpret_cast<volatile unsigned long long*>(host_out) = total;
+            __threadfence_system();
+        }
+    }
 }

@@ -153,6 +153,29 @@ def test_multi_step_tracks_oracle_per_step():
     sim.close()
 
 
+def test_clustered_state_switches_to_the_tile_kernel():
+    """Blobs: most cells are empty (7 particles per cell on average -> the per-particle kernel on the
+    first step) but most particles sit in cells with hundreds.  The occupancy measured by a step
+    (sum n_c^2 / n, taken over at the next synchronising call) moves the following steps to the
+    generation-4 tile kernel; every step still matches the oracle."""
+    p, table, radio = U.config("eater")
+    state, counts = U.random_state(60000, 6, 12, p.canvas, "blobs")
+    sim = make_sim(p, table, radio, state, counts)
+    used = []
+    for step in range(3):
+        before = sim.getParticleData()
+        cprev = sim.getNeighborCounts()
+        sim.simulate()
+        used.append(sim.stats().force_kernel)
+        got, gcnt = sim.getParticleData(), sim.getNeighborCounts()
+        want, wcnt, fabs = O.step(before, cprev, p, table, radio, "cells", THREADS)
+        assert np.array_equal(gcnt, wcnt), step
+        mult = U.force_multiplier_of(p, wcnt, cprev)
+        assert U.force_rel_err(got["acc"], want["acc"], fabs, mult).max() <= U.FORCE_RTOL
+    assert used[0] == 1 and used[-1] == 3, used
+    sim.close()
+
+
 def test_simulate_n_steps_equals_n_calls():
     p, table, radio = U.config("eater")
     state, counts = U.random_state(5000, 6, 3, p.canvas, "cube")
