@@ -184,6 +184,9 @@ def run_ours(args):
         sim.setOption("graph_kernel", args.graph_kernel)
     if args.no_graphs:
         sim.setOption("cuda_graphs", 0)
+    for kv in args.opt:
+        k, v = kv.split("=")
+        sim.setOption(k, float(v))
     sim.setOption("timing", 2)   # whole-step events; the step itself replays a CUDA graph
 
     def one_step():
@@ -445,6 +448,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--graph-kernel", type=int, default=0, help="0 auto, 1 thread per particle, 2 warp per particle")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--opt", action="append", default=[], help="engine option name=value (experiments)")
     ap.add_argument("--no-graphs", action="store_true", help="launch every kernel individually")
     ap.add_argument("--ref-cpu", action="store_true", help="reference arm on the CPU oracle port instead")
     args = ap.parse_args()

@@ -179,6 +179,7 @@ struct cf_sim {
     // options
     int opt_force_kernel = 0; // 0 auto, 1 per-particle, 2 tile (generation 3), 3 tile (generation 4)
     int opt_timing = 0;
+    int opt_t4_ctas = 0;      // experiment: resident CTAs per SM of the generation-4 tile kernel (0 = default 5)
     double opt_max_cells_per_particle = 16.0; // fine grids pay off for clustered states (cells are cheap)
 
     // stats
@@ -1044,12 +1045,19 @@ static int launch_force(cf_sim* s) {
                s->sc.x_off + s->sc.x_cells - 1,
                s->sc.dims[1] * s->sc.dims[2], s->d_tiles, s->d_tile_ctrl);
         if (kernel == 3) { // persistent grid: 5 CTAs of 4 independent warps per SM (96 registers per thread)
-            const int grid = s->sm_count * 5;
+            // experiment knob (cf_set_option "t4_ctas_per_sm"): fewer resident CTAs, enforced with dynamic shared memory
+            const int ctas = s->opt_t4_ctas > 0 ? std::min(s->opt_t4_ctas, 5) : 5;
+            const int grid = s->sm_count * ctas;
+            const size_t pad = ctas < 5 ? (size_t)(220 * 1024 / ctas) - 36 * 1024 : 0;
+            if (pad) {
+                cudaFuncSetAttribute(force_tile4_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad);
+                cudaFuncSetAttribute(force_tile4_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad);
+            }
             if (homog)
-                LAUNCH(s, force_tile4_kernel<1>, grid, T4_WARPS * 32, 0, pos, s->cell_start, s->h_pos, s->h_start,
+                LAUNCH(s, force_tile4_kernel<1>, grid, T4_WARPS * 32, pad, pos, s->cell_start, s->h_pos, s->h_start,
                        s->d_tiles, s->d_tile_ctrl, s->frc, s->sc, s->d_tables);
             else
-                LAUNCH(s, force_tile4_kernel<0>, grid, T4_WARPS * 32, 0, pos, s->cell_start, pos, s->cell_start,
+                LAUNCH(s, force_tile4_kernel<0>, grid, T4_WARPS * 32, pad, pos, s->cell_start, pos, s->cell_start,
                        s->d_tiles, s->d_tile_ctrl, s->frc, s->sc, s->d_tables);
             return 0;
         }
@@ -1095,7 +1103,7 @@ static std::vector<char> step_signature(const cf_sim* s) {
                           s->h_comp, s->h_start};
     put(ptrs, sizeof(ptrs));
     int ints[] = {s->n, s->ncell, s->cur, s->opt_force_kernel, s->sorted_valid ? 1 : 0, s->half_bound_ok ? 1 : 0,
-                  s->planned_force_kernel};
+                  s->planned_force_kernel, s->opt_t4_ctas};
     put(ints, sizeof(ints));
     return sig;
 }
@@ -1519,6 +1527,7 @@ extern "C" int cf_set_option(cf_sim* s, const char* name, double value) {
     if (k == "force_kernel") s->opt_force_kernel = (int)value;
     else if (k == "graph_kernel") s->opt_graph_kernel = (int)value; // 0 auto, 1 thread per particle, 2 warp per particle
     else if (k == "timing") s->opt_timing = (int)value;
+    else if (k == "t4_ctas_per_sm") s->opt_t4_ctas = (int)value;
     else if (k == "max_cells_per_particle") s->opt_max_cells_per_particle = value;
     else if (k == "cuda_graphs") s->opt_graphs = (int)value;
     else if (k == "global_particle_count") s->n_total = (long long)value; // same value on every rank

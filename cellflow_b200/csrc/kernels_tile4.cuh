@@ -139,7 +139,7 @@ __device__ __forceinline__ void t4_live(u64 dxa, u64 dya, u64 dza, u64 d2a, u64 
 template <int MODE, bool WRAP>
 __device__ __forceinline__ void t4_chunk(unsigned sbase, const unsigned (&live)[TK_IPT], const float (&npx)[TK_IPT],
                                          const float (&npy)[TK_IPT], const float (&npz)[TK_IPT], unsigned tis4,
-                                         unsigned s_tab_addr, const float4* __restrict__ cst, float sx, float sy,
+                                         unsigned s_tab_addr, unsigned cst_addr, float sx, float sy,
                                          float sz, float cutu, float c2u, float pau, float pbu,
                                          T4AccScalar (&acc)[TK_IPT], int (&cnt)[TK_IPT]) {
     const u64 sx2 = tk_pack(sx, sx), sy2 = tk_pack(sy, sy), sz2 = tk_pack(sz, sz);
@@ -168,7 +168,8 @@ __device__ __forceinline__ void t4_chunk(unsigned sbase, const unsigned (&live)[
             // (measured: eater 4.89 -> 4.76 ms without it, pulser 1.96 -> 2.30 ms without it)
             if (MODE == 0 && !(live[k] & bit)) continue;
             float4 cs = make_float4(c2u, pau, pbu, cutu);
-            if (MODE == 1) cs = cst[k * 32];
+            if (MODE == 1) // (c2, A, B, cut2) of (layer k, this lane): 32-bit shared address, no generic pointer
+                asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(cs.x), "=f"(cs.y), "=f"(cs.z), "=f"(cs.w) : "r"(cst_addr + 512u * k));
             const u64 px = tk_pack(npx[k], npx[k]), py = tk_pack(npy[k], npy[k]), pz = tk_pack(npz[k], npz[k]);
             u64 dxa = tk_add2(xa, px), dxb = tk_add2(xb, px);
             u64 dya = tk_add2(ya, py), dyb = tk_add2(yb, py);
@@ -224,7 +225,7 @@ force_tile4_kernel(const float4* __restrict__ pos4, const int* __restrict__ cell
     const float c2u = c.nk_log2e * c.inv_reff_uniform * c.inv_reff_uniform;
     const float pau = c.repulsion, pbu = -(c.attraction * c.inv_reff_uniform);
     int2* const wsub = &sm.sub[warp][0];
-    float4* const wcst = &sm.cst[MODE ? warp : 0][0][lane];
+    const unsigned cst_addr = (unsigned)__cvta_generic_to_shared(&sm.cst[MODE ? warp : 0][0][lane]); // + 512 * layer
     const unsigned s_tab_addr = (unsigned)__cvta_generic_to_shared(s_tab);
     const unsigned stage_addr = (unsigned)__cvta_generic_to_shared(&sm.x[warp][0][0]); // + buf*256 + 4*slot
     constexpr unsigned STRIDE = T4_WARPS * 2 * T4_JC * 4;
@@ -406,7 +407,7 @@ force_tile4_kernel(const float4* __restrict__ pos4, const int* __restrict__ cell
                     for (int k = 0; k < TK_IPT; k++) {
                         float4 e = *reinterpret_cast<const float4*>(row + ((tis4 >> (8 * k)) & 255u) * 4u);
                         if (!(k * 32 + lane < ni)) e.w = 0.f; // no particle: never accepts
-                        wcst[k * 32] = e;
+                        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(cst_addr + 512u * k), "f"(e.x), "f"(e.y), "f"(e.z), "f"(e.w) : "memory");
                         const float mx = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(e.w))); // cut2 >= 0
                         if (lane == 0) sm.box[warp][k][0].w = mx * 1.0001f + 0.01f;
                     }
@@ -425,10 +426,10 @@ force_tile4_kernel(const float4* __restrict__ pos4, const int* __restrict__ cell
             }
             if (live[0] | live[1] | live[2] | live[3]) {
                 if (wrap)
-                    t4_chunk<MODE, true>(sbase, live, npx, npy, npz, tis4, s_tab_addr, wcst, sx, sy, sz, cutu, c2u, pau, pbu,
+                    t4_chunk<MODE, true>(sbase, live, npx, npy, npz, tis4, s_tab_addr, cst_addr, sx, sy, sz, cutu, c2u, pau, pbu,
                                          acc, cnt);
                 else
-                    t4_chunk<MODE, false>(sbase, live, npx, npy, npz, tis4, s_tab_addr, wcst, sx, sy, sz, cutu, c2u, pau,
+                    t4_chunk<MODE, false>(sbase, live, npx, npy, npz, tis4, s_tab_addr, cst_addr, sx, sy, sz, cutu, c2u, pau,
                                           pbu, acc, cnt);
             }
             buf ^= 1; // the other buffer was last read one chunk ago by this same warp

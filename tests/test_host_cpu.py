@@ -147,3 +147,23 @@ def test_product_does_not_import_oracle():
                 text = open(os.path.join(root, f), errors="replace").read()
                 assert "liboracle" not in text and "import oracle" not in text, f
                 assert "cellflow_oracle" not in text or f.endswith((".cuh",)), f
+
+
+def test_hilbert_table_is_a_space_filling_curve():
+    """The 64-byte table of csrc/cf_device.cuh (cf_hilbert64) against the independent restatement in
+    tests/util.py: a bijection onto 0..63 whose consecutive sub-cells are face neighbours."""
+    import re
+    import util as U
+    src = open(os.path.join(U.ROOT, "cellflow_b200", "csrc", "cf_device.cuh")).read()
+    body = src[src.index("cf_hilbert64("):src.index("cf_sort_key(")]
+    words = [int(w, 16) for w in re.findall(r"v = (0x[0-9a-f]{8})u", body)]
+    assert len(words) == 16
+    table = np.array([(words[i >> 2] >> (8 * (i & 3))) & 255 for i in range(64)], np.uint32)
+    g = np.arange(4)
+    sx, sy, sz = [a.ravel() for a in np.meshgrid(g, g, g, indexing="ij")]
+    want = U.hilbert64(sx, sy, sz)
+    assert np.array_equal(table[(sx << 4) | (sy << 2) | sz], want)
+    assert sorted(want.tolist()) == list(range(64))
+    order = np.argsort(want)
+    pts = np.stack([sx, sy, sz], 1)[order]
+    assert np.abs(np.diff(pts, axis=0)).sum(1).max() == 1

@@ -207,14 +207,12 @@ def test_cell_assignment_bit_exact():
     sim = make_sim(p, table, radio, state, counts)
     keys, ids = sim.cellKeys()
     dims = np.int32(list(sim.stats().grid))
-    # key = cell*64 + Morton code of the 4x4x4 sub-cell (z bit lowest)
+    # key = cell*64 + Hilbert index of the 4x4x4 sub-cell
     inv = dims.astype(np.float32) / p.canvas
     y = (state["pos"] * inv).astype(np.float32)
     cell3 = np.minimum(y.astype(np.int32), dims - 1)
     sub = np.clip(np.minimum((y * np.float32(4)).astype(np.int32), 4 * dims - 1) - 4 * cell3, 0, 3).astype(np.uint32)
-    spread = lambda v: (v & 1) | ((v & 2) << 2)
-    morton = spread(sub[:, 2]) | (spread(sub[:, 1]) << 1) | (spread(sub[:, 0]) << 2)
-    want = O.cell_keys(state, p.canvas, dims) * np.uint32(64) + morton
+    want = O.cell_keys(state, p.canvas, dims) * np.uint32(64) + U.hilbert64(sub[:, 0], sub[:, 1], sub[:, 2])
     assert sorted(ids.tolist()) == list(range(len(state)))          # a permutation
     assert np.array_equal(keys, want[ids])                          # key of every slot
     assert np.all(np.diff(keys.astype(np.int64)) >= 0)              # sorted

@@ -105,3 +105,35 @@ def wrapped_abs_diff(a, b, canvas):
 
 def edge_set(edges):
     return set(zip(edges["i"].tolist(), edges["j"].tolist()))
+
+
+def hilbert64(sx, sy, sz):
+    """Hilbert index of the 4x4x4 sub-cell (sx, sy, sz) — Skilling's axes-to-transpose transform, 2 bits per
+    axis, restated independently of the byte table in csrc/cf_device.cuh (cf_hilbert64)."""
+    X = [np.asarray(sx, np.int64).copy(), np.asarray(sy, np.int64).copy(), np.asarray(sz, np.int64).copy()]
+    bits, n = 2, 3
+    M = 1 << (bits - 1)
+    Q = M
+    while Q > 1:
+        P = Q - 1
+        for i in range(n):
+            m = (X[i] & Q) != 0
+            X[0] = np.where(m, X[0] ^ P, X[0])
+            t = np.where(m, 0, (X[0] ^ X[i]) & P)
+            X[0] ^= t
+            X[i] ^= t
+        Q >>= 1
+    for i in range(1, n):
+        X[i] ^= X[i - 1]
+    t = np.zeros_like(X[0])
+    Q = M
+    while Q > 1:
+        t = np.where((X[n - 1] & Q) != 0, t ^ (Q - 1), t)
+        Q >>= 1
+    for i in range(n):
+        X[i] ^= t
+    h = np.zeros_like(X[0])
+    for b in range(bits - 1, -1, -1):
+        for i in range(n):
+            h = (h << 1) | ((X[i] >> b) & 1)
+    return h.astype(np.uint32)
