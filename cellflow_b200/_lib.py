@@ -9,7 +9,8 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIBPATH = os.path.join(_HERE, "lib", "libcellflow_b200.so")
+# CELLFLOW_B200_LIB: another build of the same library (kernel A/B experiments, tools/r02_ab.sh)
+_LIBPATH = os.environ.get("CELLFLOW_B200_LIB") or os.path.join(_HERE, "lib", "libcellflow_b200.so")
 
 MAX_TYPES = 10
 MAX_GRAPH_CONN = 16

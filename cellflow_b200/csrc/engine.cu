@@ -478,16 +478,53 @@ static int prepare_step_const(cf_sim* s) {
 // ---------------------------------------------------------------------------------------------
 // cell-list build
 // ---------------------------------------------------------------------------------------------
-// Items per sort block: 4096 for large inputs (<= 1024 blocks, small histograms); small inputs get
-// smaller blocks so that about one block per SM exists.
-static int sort_items_per_block(int n) {
-    int items = 4096;
-    // small inputs: about 48 blocks -- the pass is bound by its single-block scan of 256 * nblocks
-    // counters (14 us for 196 blocks at 100 k keys, one 16 k tile for <= 64 blocks), not by the
-    // histogram / scatter kernels
-    while (items > 256 && div_up(n, items) < 48) items /= 2;
-    while (div_up(n, items) > 1024) items *= 2;
-    return items;
+// Stable radix sort of (key, val) pairs (kernels_sort.cuh).  The pairs are in k[0]/v[0] — or, with GEN,
+// generated by the first pass from `fn` (keys) and the identity permutation (vals) into k[0]/v[0].  The
+// element count is n_upper, or *dn (<= n_upper) when dn is a device pointer.  Returns in *out_src the
+// index (0/1) of the buffer pair holding the result.
+template <class KeyFn, bool GEN>
+static int radix_sort_run(cf_sim* s, KeyFn fn, uint32_t* k[2], uint32_t* v[2], int n_upper, const int* dn,
+                          long long key_range, int* out_src) {
+    const RsPlan P = rs_make_plan(n_upper, key_range);
+    const size_t hist_need = (size_t)RS_MAX_BINS * P.nblocks + RS_MAX_BINS;
+    if (hist_need > s->hist_cap) {
+        CU(cudaStreamSynchronize(s->stream));
+        cudaFree(s->hist);
+        s->hist = nullptr;
+        s->hist_cap = hist_need * 2;
+        CU(cudaMalloc(&s->hist, s->hist_cap * sizeof(uint32_t)));
+    }
+    uint32_t* totals = s->hist + (size_t)RS_MAX_BINS * P.nblocks;
+    int src = 0;
+    for (int p = 0; p < P.passes; p++) {
+        const int shift = p * P.bits_per_pass;
+        const uint32_t mask = (1u << P.bits_per_pass) - 1u;
+        if (p == 0)
+            LAUNCH(s, (rs_hist_kernel<KeyFn, GEN>), P.nblocks, RS_THREADS, 0, fn, k[0], v[0], n_upper, dn, shift, mask,
+                   s->hist, P.nblocks, P.items);
+        else
+            LAUNCH(s, (rs_hist_kernel<RsKeysFromArray, false>), P.nblocks, RS_THREADS, 0, RsKeysFromArray{k[src]},
+                   nullptr, nullptr, n_upper, dn, shift, mask, s->hist, P.nblocks, P.items);
+        LAUNCH(s, rs_scan_rows_kernel, (int)mask + 1, RS_THREADS, 0, s->hist, P.nblocks, totals);
+#define RS_SCATTER(R_)                                                                                          \
+    LAUNCH(s, rs_scatter_kernel<R_>, P.nblocks, RS_THREADS, 0, k[src], v[src], k[src ^ 1], v[src ^ 1], n_upper, \
+           dn, shift, mask, s->hist, totals, P.nblocks, P.groups)
+        switch (P.R) {
+            case 1: RS_SCATTER(1); break;
+            case 2: RS_SCATTER(2); break;
+            case 4: RS_SCATTER(4); break;
+            default: RS_SCATTER(8); break;
+        }
+#undef RS_SCATTER
+        src ^= 1;
+    }
+    *out_src = src;
+    return 0;
+}
+
+static int radix_sort_pairs(cf_sim* s, uint32_t* k[2], uint32_t* v[2], int n, long long key_range, int* out_src,
+                            const int* dn = nullptr) {
+    return radix_sort_run<RsKeysFromArray, false>(s, RsKeysFromArray{k[0]}, k, v, n, dn, key_range, out_src);
 }
 
 static int ensure_sorted(cf_sim* s) {
@@ -495,35 +532,14 @@ static int ensure_sorted(cf_sim* s) {
     int n = s->n;
     if (n <= 0) return 0;
     int cur = s->cur, nxt = cur ^ 1;
-    int blocks = div_up(n, 256);
-    LAUNCH(s, cell_key_kernel, blocks, 256, 0, s->pos[cur], s->keys[0], s->vals[0], n, s->sc);
-    int bits = 1;
-    while ((1ll << bits) < (long long)s->ncell * CF_KEY_SUB) bits++;
-    int passes = div_up(bits, 8);
-    int bits_per_pass = div_up(bits, passes);
-    int items = sort_items_per_block(n);
-    int nblocks = div_up(n, items);
-    size_t hist_need = (size_t)RS_BINS * nblocks;
-    if (hist_need > s->hist_cap) {
-        cudaFree(s->hist);
-        s->hist = nullptr;
-        s->hist_cap = hist_need * 2;
-        CU(cudaMalloc(&s->hist, s->hist_cap * sizeof(uint32_t)));
-    }
     int src = 0;
-    for (int p = 0; p < passes; p++) {
-        int shift = p * bits_per_pass;
-        uint32_t mask = (1u << bits_per_pass) - 1u;
-        LAUNCH(s, rs_hist_kernel, nblocks, RS_THREADS, 0, s->keys[src], n, shift, mask, s->hist, nblocks, items);
-        LAUNCH(s, rs_scan_kernel, 1, 1024, 0, s->hist, RS_BINS * nblocks);
-        LAUNCH(s, rs_scatter_kernel, nblocks, RS_THREADS, 0, s->keys[src], s->vals[src], s->keys[src ^ 1],
-               s->vals[src ^ 1], n, shift, mask, s->hist, nblocks, items);
-        src ^= 1;
-    }
-    LAUNCH(s, reorder_kernel, blocks, 256, 0, s->vals[src], s->pos[cur], s->vel[cur], s->id[cur],
-           s->pos[nxt], s->vel[nxt], s->id[nxt], n);
-    LAUNCH(s, cell_bounds_kernel, div_up(s->ncell + 1, 256), 256, 0, s->keys[src], n, s->cell_start,
-           s->ncell, 0);
+    // key generation is fused into the first histogram pass
+    if (int rc = radix_sort_run<CellKeyFn, true>(s, CellKeyFn{s->pos[cur], s->sc}, s->keys, s->vals, n, nullptr,
+                                                 (long long)s->ncell * CF_KEY_SUB, &src))
+        return rc;
+    LAUNCH(s, reorder_bounds_kernel, div_up(std::max(n, s->ncell + 1), 256), 256, 0, s->vals[src], s->keys[src],
+           s->pos[cur], s->vel[cur], s->id[cur], s->pos[nxt], s->vel[nxt], s->id[nxt], n, nullptr, s->cell_start,
+           s->ncell, 0, nullptr);
     if (src != 0) std::swap(s->keys[0], s->keys[1]), std::swap(s->vals[0], s->vals[1]);
     // keys[0] now holds the sorted keys of the current order
     s->cur = nxt;
@@ -1046,9 +1062,9 @@ static int launch_force(cf_sim* s) {
                s->sc.dims[1] * s->sc.dims[2], s->d_tiles, s->d_tile_ctrl);
         if (kernel == 3) { // persistent grid: 5 CTAs of 4 independent warps per SM (96 registers per thread)
             // experiment knob (cf_set_option "t4_ctas_per_sm"): fewer resident CTAs, enforced with dynamic shared memory
-            const int ctas = s->opt_t4_ctas > 0 ? std::min(s->opt_t4_ctas, 5) : 5;
+            const int ctas = s->opt_t4_ctas > 0 ? std::min(s->opt_t4_ctas, T4_MINB) : T4_MINB;
             const int grid = s->sm_count * ctas;
-            const size_t pad = ctas < 5 ? (size_t)(220 * 1024 / ctas) - 36 * 1024 : 0;
+            const size_t pad = ctas < T4_MINB ? (size_t)(220 * 1024 / ctas) - 36 * 1024 : 0;
             if (pad) {
                 cudaFuncSetAttribute(force_tile4_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad);
                 cudaFuncSetAttribute(force_tile4_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad);

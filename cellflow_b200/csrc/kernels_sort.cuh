@@ -1,170 +1,236 @@
-// kernels_sort.cuh — stable LSD radix sort of (cell key, slot) pairs: the cell-list build.
+// kernels_sort.cuh — stable LSD radix sort of (key, slot) pairs: the cell-list build (HBM-bound).
 //
-// Keys are cell indices (< ncell), so only ceil(log2(ncell)) bits are sorted, in passes of at
-// most 8 bits.  Each pass is histogram -> exclusive scan -> stable scatter; the sort is stable
-// and therefore deterministic: the slot order inside a cell (hence the force summation order)
-// is a pure function of the input, run to run and rank to rank.
+// Keys are small (cell * 64 + Hilbert sub-cell < 2^18 at the bench default, type * ncell + cell for the
+// proximity graph), so only ceil(log2(range)) bits are sorted, in passes of up to RS_MAX_BITS = 9 bits
+// (two passes for <= 2^18 keys).  Each pass is
+//     per-block digit histogram -> one scan block PER DIGIT (parallel) -> stable scatter,
+// and the sort is stable and therefore deterministic: the slot order inside a cell (hence the force
+// summation order) is a pure function of the input, run to run and rank to rank.
 //
-// HBM traffic per pass: histogram reads 4 B/key; scatter reads 8 B and writes 8 B per pair.
+// Round 2 (VERDICT r01 "radix sort at roofline"): the single-block scan of all 256 * nblocks counters
+// (16 us of a 44 us pass) is gone — digit row d is scanned by its own block and the 512 digit totals are
+// scanned again by every scatter block in shared memory; 9-bit digits make the 18-bit cell key two passes
+// instead of three; the first pass generates its keys on the fly from the positions (KeyFn) instead of
+// reading a key array another kernel wrote; a scatter thread loads all its (key, value) pairs before the
+// first barrier (one exposed memory latency per block instead of one per round); blocks are sized for
+// >= 2 waves of CTAs.  The element count may live on the device (`dn`): the multi-GPU slab step never
+// tells the host how many particles a rank owns (csrc/slab_host.inl).
+//
+// HBM traffic per pass: histogram reads 4 B/key (16 B position in the fused first pass); scatter reads
+// 8 B and writes 8 B per pair.
 #pragma once
 #include "cf_device.cuh"
 
 #define RS_THREADS 256
 #define RS_WARPS (RS_THREADS / 32)
-#define RS_BINS 256
+#define RS_MAX_BITS 9
+#define RS_MAX_BINS (1 << RS_MAX_BITS)
 
-// hist[d * nblocks + b] = number of keys of block b whose digit is d.
+// Key sources of the histogram kernel -----------------------------------------------------------
+struct RsKeysFromArray { // later passes: the keys the previous scatter wrote
+    const uint32_t* keys;
+    __device__ __forceinline__ uint32_t operator()(int i) const { return keys[i]; }
+};
+
+__device__ __forceinline__ int rs_count(const int* dn, int n_upper) {
+    if (!dn) return n_upper;
+    const int v = *dn;
+    return v < n_upper ? (v < 0 ? 0 : v) : n_upper;
+}
+
+// hist[d * nblocks + b] = number of keys of block b whose digit is d.  GEN: the keys come from `fn`
+// (computed from the particle state) and are written to keys_out together with the identity permutation.
+template <class KeyFn, bool GEN>
 __global__ void __launch_bounds__(RS_THREADS)
-rs_hist_kernel(const uint32_t* __restrict__ keys, int n, int shift, uint32_t mask,
-               uint32_t* __restrict__ hist, int nblocks, int items_per_block) {
-    __shared__ uint32_t sh[RS_BINS];
-    sh[threadIdx.x] = 0;
+rs_hist_kernel(KeyFn fn, uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, int n_upper,
+               const int* __restrict__ dn, int shift, uint32_t mask, uint32_t* __restrict__ hist, int nblocks,
+               int items_per_block) {
+    __shared__ uint32_t sh[RS_MAX_BINS];
+    const int n = rs_count(dn, n_upper);
+    const int nbins = (int)mask + 1;
+    for (int d = threadIdx.x; d < nbins; d += RS_THREADS) sh[d] = 0;
     __syncthreads();
-    int base = blockIdx.x * items_per_block;
-    int end = min(base + items_per_block, n);
-    for (int i = base + threadIdx.x; i < end; i += RS_THREADS) {
-        uint32_t d = (keys[i] >> shift) & mask;
-        // warp-aggregate: nearly-sorted input puts whole warps into one bin
-        uint32_t peers = __match_any_sync(__activemask(), d);
-        if ((peers & ((1u << (threadIdx.x & 31)) - 1u)) == 0) atomicAdd(&sh[d], __popc(peers));
+    const int base = blockIdx.x * items_per_block;
+    const int end = min(base + items_per_block, n);
+    // four independent key loads / generations in flight per thread
+    // (uniform trip count: match_any below names the whole warp)
+    for (int b0 = base; b0 < end; b0 += 4 * RS_THREADS) {
+        const int i0 = b0 + threadIdx.x;
+        uint32_t key[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int i = i0 + u * RS_THREADS;
+            key[u] = i < end ? fn(i) : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int i = i0 + u * RS_THREADS;
+            const bool valid = i < end;
+            if (GEN && valid) {
+                keys_out[i] = key[u];
+                vals_out[i] = (uint32_t)i;
+            }
+            const uint32_t d = valid ? ((key[u] >> shift) & mask) : (uint32_t)RS_MAX_BINS;
+            // warp-aggregate: nearly-sorted input puts whole warps into one bin
+            const uint32_t peers = __match_any_sync(0xffffffffu, d);
+            if (valid && (peers & ((1u << (threadIdx.x & 31)) - 1u)) == 0) atomicAdd(&sh[d], __popc(peers));
+        }
     }
     __syncthreads();
-    hist[threadIdx.x * nblocks + blockIdx.x] = sh[threadIdx.x];
+    for (int d = threadIdx.x; d < nbins; d += RS_THREADS) hist[d * nblocks + blockIdx.x] = sh[d];
 }
 
-// In-place exclusive scan of `total` counters by one block of 1024 threads, in coalesced tiles of
-// 16384 (four uint4 per thread, each uint4 load/store warp-contiguous): thread-local prefix,
-// warp shuffle scan, 32 warp totals scanned by warp 0, running carry between tiles.  (A
-// chunk-per-thread version read with a stride of total/1024 words and took 52 us for 62 k
-// counters; a 4096-wide tiled one was bound by its three barriers per tile.)
-#define RS_SCAN_VEC 4
-__global__ void __launch_bounds__(1024) rs_scan_kernel(uint32_t* __restrict__ hist, int total) {
-    __shared__ uint32_t warp_sums[32];
-    __shared__ uint32_t carry_s;
+// Block d: exclusive scan (in place) of digit row d = hist[d * nblocks .. + nblocks), total -> totals[d].
+__global__ void __launch_bounds__(RS_THREADS) rs_scan_rows_kernel(uint32_t* __restrict__ hist, int nblocks,
+                                                                 uint32_t* __restrict__ totals) {
+    __shared__ uint32_t warp_sums[RS_WARPS];
+    uint32_t* row = hist + (size_t)blockIdx.x * nblocks;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) carry_s = 0;
-    __syncthreads();
-    const bool vec_ok = (total & 3) == 0;
-    for (int base = 0; base < total; base += 4096 * RS_SCAN_VEC) {
-        // thread owns RS_SCAN_VEC groups of 4 consecutive counters: group g starts at
-        // base + g*4096 + 4*tid, so the scan order inside a tile is (g, tid, element)
-        uint32_t v[RS_SCAN_VEC][4];
-        uint32_t gsum[RS_SCAN_VEC];
+    const int per = (nblocks + RS_THREADS - 1) / RS_THREADS; // consecutive counters per thread
+    const int i0 = tid * per, i1 = min(i0 + per, nblocks);
+    uint32_t sum = 0;
+    for (int i = i0; i < i1; i++) sum += row[i];
+    uint32_t incl = sum;
 #pragma unroll
-        for (int g = 0; g < RS_SCAN_VEC; g++) {
-            const int i = base + g * 4096 + 4 * tid;
-            v[g][0] = v[g][1] = v[g][2] = v[g][3] = 0;
-            if (vec_ok && i + 3 < total) {
-                uint4 q = *reinterpret_cast<const uint4*>(hist + i);
-                v[g][0] = q.x, v[g][1] = q.y, v[g][2] = q.z, v[g][3] = q.w;
-            } else {
-#pragma unroll
-                for (int e = 0; e < 4; e++)
-                    if (i + e < total) v[g][e] = hist[i + e];
-            }
-            gsum[g] = v[g][0] + v[g][1] + v[g][2] + v[g][3];
-        }
-        const uint32_t carry = carry_s; // final since the barrier that ended the previous tile
-        // inclusive scan of every group across the block (4 independent scans share the barriers)
-        uint32_t incl[RS_SCAN_VEC];
-#pragma unroll
-        for (int g = 0; g < RS_SCAN_VEC; g++) {
-            uint32_t x = gsum[g];
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                uint32_t t = __shfl_up_sync(0xffffffffu, x, o);
-                if (lane >= o) x += t;
-            }
-            incl[g] = x;
-        }
-        __shared__ uint32_t ws[RS_SCAN_VEC][32];
-        if (lane == 31) {
-#pragma unroll
-            for (int g = 0; g < RS_SCAN_VEC; g++) ws[g][warp] = incl[g];
-        }
-        __syncthreads();
-        if (warp < RS_SCAN_VEC) { // warp g scans the 32 warp totals of group g
-            uint32_t w = ws[warp][lane], wi = w;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                uint32_t t = __shfl_up_sync(0xffffffffu, wi, o);
-                if (lane >= o) wi += t;
-            }
-            ws[warp][lane] = wi - w;
-            if (lane == 31) warp_sums[warp] = wi; // total of group `warp`
-        }
-        __syncthreads();
-        uint32_t gbase = carry;
-#pragma unroll
-        for (int g = 0; g < RS_SCAN_VEC; g++) {
-            const int i = base + g * 4096 + 4 * tid;
-            uint32_t run = gbase + ws[g][warp] + incl[g] - gsum[g];
-            if (vec_ok && i + 3 < total) {
-                uint4 o4 = make_uint4(run, run + v[g][0], run + v[g][0] + v[g][1], run + v[g][0] + v[g][1] + v[g][2]);
-                *reinterpret_cast<uint4*>(hist + i) = o4;
-            } else {
-                uint32_t r = run;
-#pragma unroll
-                for (int e = 0; e < 4; e++) {
-                    if (i + e < total) hist[i + e] = r;
-                    r += v[g][e];
-                }
-            }
-            gbase += warp_sums[g];
-        }
-        __syncthreads(); // everyone has read ws / warp_sums / carry_s
-        if (tid == 0) carry_s = gbase;
-        __syncthreads();
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
     }
+    if (lane == 31) warp_sums[warp] = incl;
+    __syncthreads();
+    uint32_t wbase = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < RS_WARPS; w++) {
+        const uint32_t v = warp_sums[w];
+        if (w < warp) wbase += v;
+        total += v;
+    }
+    uint32_t run = wbase + incl - sum;
+    for (int i = i0; i < i1; i++) {
+        const uint32_t v = row[i];
+        row[i] = run;
+        run += v;
+    }
+    if (tid == 0) totals[blockIdx.x] = total;
 }
 
-// Stable scatter.  A block walks its items in rounds of RS_THREADS, in index order.  Per round:
-// every warp ranks its lanes per digit with match_any, the first lane of each digit group
-// publishes the group size, thread d (owner of digit d) turns the 8 per-warp sizes into bases
-// on top of the scanned histogram plus what earlier rounds of this block already placed.
+// Stable scatter.  A block owns items_per_block = 256 * R * groups consecutive items; per group, warp w
+// owns the 32 * R consecutive items [w * 32R, (w+1) * 32R) and walks them in R rounds of 32 (item r * 32 +
+// lane), so the block's order is (warp, round, lane).  A round ranks its 32 keys with match_any on top of
+// the warp's PRIVATE digit counters in shared memory — no block barrier per round (the round-1 kernel had
+// two per 256 items and updated all 8 x 256 counters every round).  After the R rounds one pass over the
+// 8 x nbins counters (two digits per thread) turns them into output bases: scanned histogram + what earlier
+// groups of this block placed + the warps before.  Three barriers per group.
+template <int R>
 __global__ void __launch_bounds__(RS_THREADS)
 rs_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
-                  uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, int n, int shift,
-                  uint32_t mask, const uint32_t* __restrict__ hist, int nblocks, int items_per_block) {
-    __shared__ uint32_t cnt[2][RS_WARPS][RS_BINS];
-    int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int w = 0; w < RS_WARPS; w++) {
-        cnt[0][w][tid] = 0;
-        cnt[1][w][tid] = 0;
-    }
-    uint32_t running = hist[tid * nblocks + blockIdx.x]; // digit `tid`: next free output slot
-    __syncthreads();
-    int base = blockIdx.x * items_per_block;
-    int rounds = items_per_block / RS_THREADS;
-    for (int r = 0; r < rounds; r++) {
-        int buf = r & 1;
-        int i = base + r * RS_THREADS + tid;
-        bool valid = i < n;
-        uint32_t key = valid ? keys_in[i] : 0xffffffffu;
-        uint32_t val = valid ? vals_in[i] : 0u;
-        uint32_t d = valid ? ((key >> shift) & mask) : RS_BINS; // invalid lanes group apart
-        uint32_t peers = __match_any_sync(0xffffffffu, d);
-        uint32_t rank = __popc(peers & ((1u << lane) - 1u));
-        if (valid && rank == 0) cnt[buf][warp][d] = __popc(peers);
+                  uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, int n_upper,
+                  const int* __restrict__ dn, int shift, uint32_t mask, const uint32_t* __restrict__ hist,
+                  const uint32_t* __restrict__ totals, int nblocks, int groups) {
+    __shared__ uint32_t cnt[RS_WARPS][RS_MAX_BINS];
+    __shared__ uint32_t running[RS_MAX_BINS]; // digit d: next free output slot of this block
+    __shared__ uint32_t wsum[RS_WARPS];
+    const int n = rs_count(dn, n_upper);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nbins = (int)mask + 1;
+    const int block_base = blockIdx.x * (RS_THREADS * R * groups);
+    if (block_base >= n) return;
+    // ---- digit bases: exclusive scan of the digit totals (<= 512, two per thread) ----
+    {
+        const int d0 = 2 * tid, d1 = 2 * tid + 1;
+        const uint32_t t0 = d0 < nbins ? totals[d0] : 0u, t1 = d1 < nbins ? totals[d1] : 0u;
+        uint32_t incl = t0 + t1;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) wsum[warp] = incl;
         __syncthreads();
-        {
-            uint32_t run = running;
+        uint32_t wbase = 0;
+#pragma unroll
+        for (int w = 0; w < RS_WARPS; w++)
+            if (w < warp) wbase += wsum[w];
+        const uint32_t excl = wbase + incl - (t0 + t1);
+        if (d0 < nbins) running[d0] = excl + hist[d0 * nblocks + blockIdx.x];
+        if (d1 < nbins) running[d1] = excl + t0 + hist[d1 * nblocks + blockIdx.x];
+    }
+    const uint32_t lt = (1u << lane) - 1u;
+    for (int g = 0; g < groups; g++) {
+        const int gbase = block_base + g * (RS_THREADS * R);
+        if (gbase >= n) break; // uniform
+        for (int d = lane; d < nbins; d += 32) cnt[warp][d] = 0;
+        __syncwarp();
+        const int wbase_i = gbase + warp * (32 * R);
+        uint32_t key[R], val[R], rank[R];
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            const int i = wbase_i + r * 32 + lane;
+            const bool valid = i < n;
+            key[r] = valid ? keys_in[i] : 0xffffffffu;
+            val[r] = valid ? vals_in[i] : 0u;
+        }
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            const bool valid = wbase_i + r * 32 + lane < n;
+            const uint32_t d = valid ? ((key[r] >> shift) & mask) : (uint32_t)RS_MAX_BINS; // invalid lanes group apart
+            const uint32_t peers = __match_any_sync(0xffffffffu, d);
+            const int leader = __ffs(peers) - 1;
+            uint32_t old = 0;
+            if (valid && lane == leader) {
+                old = cnt[warp][d];
+                cnt[warp][d] = old + __popc(peers);
+            }
+            old = __shfl_sync(0xffffffffu, old, leader);
+            rank[r] = old + __popc(peers & lt);
+            __syncwarp();
+        }
+        __syncthreads();
+        for (int dd = tid; dd < nbins; dd += RS_THREADS) {
+            uint32_t run = running[dd];
 #pragma unroll
             for (int w = 0; w < RS_WARPS; w++) {
-                uint32_t c = cnt[buf][w][tid];
-                cnt[buf][w][tid] = run;
+                const uint32_t c = cnt[w][dd];
+                cnt[w][dd] = run;
                 run += c;
-                cnt[buf ^ 1][w][tid] = 0;
             }
-            running = run;
+            running[dd] = run;
         }
         __syncthreads();
-        if (valid) {
-            uint32_t dst = cnt[buf][warp][d] + rank;
-            keys_out[dst] = key;
-            vals_out[dst] = val;
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            if (wbase_i + r * 32 + lane < n) {
+                const uint32_t d = (key[r] >> shift) & mask;
+                const uint32_t dst = cnt[warp][d] + rank[r];
+                keys_out[dst] = key[r];
+                vals_out[dst] = val[r];
+            }
         }
-        // the next round writes cnt[buf^1] (zeroed above, before the barrier) and only reads
-        // cnt[buf] again two rounds later, after two more barriers
+        if (g + 1 < groups) __syncthreads(); // cnt is reset by its own warp, but `running` is read again
     }
+}
+
+// Host-side plan of one sort: passes, digit width, block shape.
+struct RsPlan {
+    int passes, bits_per_pass, R, groups, items, nblocks;
+};
+static inline RsPlan rs_make_plan(int n_upper, long long key_range) {
+    RsPlan p;
+    int bits = 1;
+    while ((1ll << bits) < key_range) bits++;
+    p.passes = (bits + RS_MAX_BITS - 1) / RS_MAX_BITS;
+    p.bits_per_pass = (bits + p.passes - 1) / p.passes;
+    // items per block = 256 * R * groups: about 4 CTAs per SM for mid-sized inputs, rows of <= 2048 blocks
+    const long long target_blocks = 148 * 4;
+    long long per = (n_upper + target_blocks - 1) / target_blocks;
+    int R = 1;
+    while (R < 8 && RS_THREADS * R < per) R *= 2;
+    int groups = 1;
+    while (((long long)n_upper + (long long)RS_THREADS * R * groups - 1) / ((long long)RS_THREADS * R * groups) > 2048) groups *= 2;
+    p.R = R;
+    p.groups = groups;
+    p.items = RS_THREADS * R * groups;
+    p.nblocks = (int)(((long long)n_upper + p.items - 1) / p.items);
+    if (p.nblocks < 1) p.nblocks = 1;
+    return p;
 }

@@ -99,16 +99,48 @@ __global__ void move_universe_kernel(float4* __restrict__ pos4, int n, float dx,
     pos4[k] = p;
 }
 
-// Sort key + identity permutation (first pass of the cell-list build); key = cf_sort_key.
-__global__ void cell_key_kernel(const float4* __restrict__ pos4, uint32_t* __restrict__ keys,
-                                uint32_t* __restrict__ vals, int n, StepConst c) {
-    int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
-    keys[k] = cf_sort_key(pos4[k], c);
-    vals[k] = (uint32_t)k;
+// Key source of the fused first sort pass (kernels_sort.cuh, rs_hist_kernel<.., true>): key = cf_sort_key.
+struct CellKeyFn {
+    const float4* pos4;
+    StepConst c;
+    __device__ __forceinline__ uint32_t operator()(int i) const { return cf_sort_key(pos4[i], c); }
+};
+
+// Reorder gather + cell bounds in one launch.
+//   thread s < n      : slot s of the new order takes old slot perm[s];
+//   thread c <= ncell : cellStart[c] = first slot whose key is >= c*64 (lower bound over the sorted keys);
+//                       cell c occupies slots [cellStart[c], cellStart[c+1]).  One thread per cell, log2(n)
+//                       probes of an L2-resident array; no worst case for clustered states (unlike a
+//                       per-particle gap fill).
+// n may live on the device (dn; slab mode).  Only the first n_keys sorted keys take part in the bounds
+// (slab mode: the leavers' keys, class >= 1, sit behind them); *n_out = cellStart[ncell] - base when given.
+__global__ void reorder_bounds_kernel(const uint32_t* __restrict__ perm, const uint32_t* __restrict__ skeys,
+                                      const float4* __restrict__ pos_in, const float4* __restrict__ vel_in,
+                                      const int* __restrict__ id_in, float4* __restrict__ pos_out,
+                                      float4* __restrict__ vel_out, int* __restrict__ id_out, int n_upper,
+                                      const int* __restrict__ dn, int* __restrict__ cell_start, int ncell, int base,
+                                      int* __restrict__ n_out) {
+    const int n = dn ? min(max(*dn, 0), n_upper) : n_upper;
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s <= ncell) {
+        const uint32_t want = (uint32_t)s * CF_KEY_SUB; // first key of cell s
+        int lo = 0, hi = n;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (skeys[mid] < want) lo = mid + 1; else hi = mid;
+        }
+        cell_start[s] = base + lo;
+        if (s == ncell && n_out) *n_out = lo;
+    }
+    if (s < n) {
+        const uint32_t src = perm[s];
+        pos_out[s] = pos_in[src];
+        vel_out[s] = vel_in[src];
+        id_out[s] = id_in[src];
+    }
 }
 
-// Reorder gather: slot s of the new order takes old slot perm[s].
+// Reorder gather alone (slab initialisation): slot s of the new order takes old slot perm[s].
 __global__ void reorder_kernel(const uint32_t* __restrict__ perm, const float4* __restrict__ pos_in,
                                const float4* __restrict__ vel_in, const int* __restrict__ id_in,
                                float4* __restrict__ pos_out, float4* __restrict__ vel_out,
@@ -119,22 +151,6 @@ __global__ void reorder_kernel(const uint32_t* __restrict__ perm, const float4* 
     pos_out[s] = pos_in[src];
     vel_out[s] = vel_in[src];
     id_out[s] = id_in[src];
-}
-
-// cellStart[c] = first slot whose key is >= c*64 (lower bound over the sorted keys), c in [0, ncell];
-// cell c occupies slots [cellStart[c], cellStart[c+1]).  One thread per cell, log2(n) probes of an
-// L2-resident array; no worst case for clustered states (unlike a per-particle gap fill).
-__global__ void cell_bounds_kernel(const uint32_t* __restrict__ skeys, int n, int* __restrict__ cell_start,
-                                   int ncell, int base) {
-    int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c > ncell) return;
-    const uint32_t want = (uint32_t)c * CF_KEY_SUB; // first key of cell c
-    int lo = 0, hi = n;
-    while (lo < hi) {
-        int mid = (lo + hi) >> 1;
-        if (skeys[mid] < want) lo = mid + 1; else hi = mid;
-    }
-    cell_start[c] = base + lo;
 }
 
 __global__ void fill_int_kernel(int* __restrict__ a, int n, int v) {

@@ -35,6 +35,9 @@
 #include "kernels_tile.cuh"
 
 #define T4_WARPS 4
+#ifndef T4_MINB
+#define T4_MINB 5 // resident CTAs per SM the register budget is set for (96 registers per thread)
+#endif
 #define T4_JC 128 // staged j per chunk and warp: one quad of 4 consecutive j per lane
 #define T4_MAXSUB (TK_MAX_RUNS * CF_T_MAX)
 #define T4_INF __int_as_float(0x7f800000)
@@ -195,7 +198,7 @@ __device__ __forceinline__ void t4_chunk(unsigned sbase, const unsigned (&live)[
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(T4_WARPS * 32, 5)
+__global__ void __launch_bounds__(T4_WARPS * 32, T4_MINB)
 force_tile4_kernel(const float4* __restrict__ pos4, const int* __restrict__ cell_start,
                    const float4* __restrict__ posj, const int* __restrict__ startj,
                    const int2* __restrict__ tiles, int* __restrict__ ctrl, float4* __restrict__ frc4, StepConst c,

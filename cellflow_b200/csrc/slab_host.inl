@@ -123,37 +123,6 @@ static int slab_mig_msg_cap(const cf_sim* s) {
     return (int)std::min<long long>(cap, s->cap_mig);
 }
 
-// Stable radix sort of (key, val) pairs held in keys[0]/vals[0] of the given buffers; returns the
-// index (0/1) of the buffer holding the result.
-static int radix_sort_pairs(cf_sim* s, uint32_t* k[2], uint32_t* v[2], int n, long long key_range, int* out_src) {
-    int bits = 1;
-    while ((1ll << bits) < key_range) bits++;
-    int passes = div_up(bits, 8);
-    int bits_per_pass = div_up(bits, passes);
-    int items = sort_items_per_block(n);
-    int nblocks = div_up(n, items);
-    size_t hist_need = (size_t)RS_BINS * nblocks;
-    if (hist_need > s->hist_cap) {
-        CU(cudaStreamSynchronize(s->stream));
-        cudaFree(s->hist);
-        s->hist = nullptr;
-        s->hist_cap = hist_need * 2;
-        CU(cudaMalloc(&s->hist, s->hist_cap * sizeof(uint32_t)));
-    }
-    int src = 0;
-    for (int p = 0; p < passes; p++) {
-        int shift = p * bits_per_pass;
-        uint32_t mask = (1u << bits_per_pass) - 1u;
-        LAUNCH(s, rs_hist_kernel, nblocks, RS_THREADS, 0, k[src], n, shift, mask, s->hist, nblocks, items);
-        LAUNCH(s, rs_scan_kernel, 1, 1024, 0, s->hist, RS_BINS * nblocks);
-        LAUNCH(s, rs_scatter_kernel, nblocks, RS_THREADS, 0, k[src], v[src], k[src ^ 1], v[src ^ 1], n, shift, mask,
-               s->hist, nblocks, items);
-        src ^= 1;
-    }
-    *out_src = src;
-    return 0;
-}
-
 static int slab_check_flags(cf_sim* s) {
     int f = s->h_slab_counts[3];
     if (f == 1) return fail(CF_ERR_STATE, "a particle moved further than one slab width in one step");
@@ -243,10 +212,9 @@ static int ensure_sorted_slab(cf_sim* s, cudaEvent_t ev_x0, cudaEvent_t ev_x1) {
         src ^= 1;
     }
     // ---- reorder into the other buffer, cell bounds of the owned layers ----
-    if (n_new > 0)
-        LAUNCH(s, reorder_kernel, div_up(n_new, 256), 256, 0, fvals, s->pos[cur] + B, s->vel[cur] + B, s->id[cur] + B,
-               s->pos[nxt] + B, s->vel[nxt] + B, s->id[nxt] + B, n_new);
-    LAUNCH(s, cell_bounds_kernel, div_up(s->ncell + 1, 256), 256, 0, fkeys, n_new, s->cell_start, s->ncell, B);
+    LAUNCH(s, reorder_bounds_kernel, div_up(std::max(n_new, s->ncell + 1), 256), 256, 0, fvals, fkeys, s->pos[cur] + B,
+           s->vel[cur] + B, s->id[cur] + B, s->pos[nxt] + B, s->vel[nxt] + B, s->id[nxt] + B, n_new, nullptr,
+           s->cell_start, s->ncell, B, nullptr);
     if (src != 0) std::swap(s->keys[0], s->keys[1]), std::swap(s->vals[0], s->vals[1]);
     s->cur = nxt;
     s->n = n_new;
