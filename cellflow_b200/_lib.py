@@ -121,7 +121,7 @@ SYMBOLS = [
     "cf_set_params", "cf_get_params", "cf_step", "cf_sync", "cf_step_host", "cf_ratio_with_lfo",
     "cf_build_graph", "cf_download_graph_edges", "cf_download_graph_vertices",
     "cf_default_params", "cf_default_preset", "cf_load_preset", "cf_save_preset",
-    "cf_apply_preset", "cf_nccl_unique_id", "cf_comm_init", "cf_init_particles_global", "cf_slab_bounds",
+    "cf_apply_preset", "cf_comm_init", "cf_comm_mailbox_handle", "cf_comm_connect", "cf_slab_set_bounds", "cf_init_particles_global", "cf_slab_bounds",
     "cf_upload_particles_ids",
     "cf_download_particles_ids", "cf_get_stats", "cf_stats_reset", "cf_download_cell_keys",
     "cf_set_option", "cf_bench_fp32_peak", "cf_bench_flush_l2", "cf_last_error", "cf_version",

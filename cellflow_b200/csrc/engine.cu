@@ -26,7 +26,6 @@
 #include "kernels_state.cuh"
 #include "kernels_tile.cuh"
 #include "kernels_tile4.cuh"
-#include "nccl_dyn.h"
 
 static_assert(sizeof(AosParticle) == 44 && sizeof(cf_particle) == 44, "reference Particle is 44 B");
 
@@ -59,9 +58,12 @@ extern "C" const char* cf_version(void) { return "cellflow_b200 0.1 (sm_100a)"; 
 // ---------------------------------------------------------------------------------------------
 // handle
 // ---------------------------------------------------------------------------------------------
+#define CF_STEP_EVENTS 8
 struct StepEvents {
-    cudaEvent_t e[6]; // begin, after cell list, after force, after integrate, exchange begin/end
-    bool has_exchange = false; // e[4], e[5] were recorded for this step
+    // begin, after cell list, after force, after integrate; slab mode: migrants emitted, arrivals appended,
+    // owned cells sorted, ghosts in place (e[4]..e[5] and e[6]..e[7] bracket the two mailbox exchanges)
+    cudaEvent_t e[CF_STEP_EVENTS];
+    bool has_exchange = false; // e[4..7] were recorded for this step
 };
 
 struct cf_sim {
@@ -146,22 +148,23 @@ struct cf_sim {
     int base = 0;            // first owned slot
     bool slab = false;
     int rank = 0, world = 1;
-    ncclComm_t comm = nullptr;
     int cap_own = 0, cap_halo = 0, cap_mig = 0;
     int nxl = 0;             // owned x layers
     SlabGeom geom;
-    char* send_mig[2] = {nullptr, nullptr};  // [0] to/from left, [1] to/from right
-    char* recv_mig[2] = {nullptr, nullptr};
-    char* send_halo[2] = {nullptr, nullptr};
-    char* recv_halo[2] = {nullptr, nullptr};
-    uint32_t* akeys[2] = {nullptr, nullptr};
-    uint32_t* avals[2] = {nullptr, nullptr};
+    std::vector<float> bounds;     // slab bounds set by cf_slab_set_bounds (empty: uniform split)
+    SlabMail mail;                 // mailbox layout (identical on every rank)
+    char* mailbox = nullptr;       // this rank's mailbox (device memory, exported through CUDA IPC)
+    char* peer_box[2] = {nullptr, nullptr}; // the left / right neighbour's mailbox, mapped into this process
+    bool connected = false;
     uint32_t* gkeys[2] = {nullptr, nullptr};
-    int* d_slab_counts = nullptr;  // [0..2] class counts, [3] error flag, [4..5] ghost counts
-    int* h_slab_counts = nullptr;  // pinned mirror
-    int n_ghost[2] = {0, 0};
+    int* d_slab = nullptr;         // device status words (kernels_slab.cuh: SLAB_NCUR ...): counts never leave the device
+    int* h_slab = nullptr;         // pinned mirror, refreshed where the API synchronises
+    int seq_mig = 0, seq_halo = 0; // sequence numbers of the two message kinds (same on every rank)
+    bool mig_sent = false;         // the last integrate already emitted this step's migrants
     long long n_total = 0;         // global particle count (slab mode)
-    double halo_slack = 2.0, mig_slack = 1.0;
+    double wait_timeout_ms = 20000.0;
+    double cell_edge = 1.0;        // cell edge and largest interaction radius of the current grid
+    float rmax = 0.f;
     double ms_exchange = 0;
 
     // CUDA graphs of the (static) single-GPU step sequence: small problems are launch-bound
@@ -383,7 +386,15 @@ static float compute_tables(cf_sim* s, DeviceTables& t, bool& uniform) {
     return rmax;
 }
 
+// x layers of a slab of width w (same rule on every rank, for every rank's slab)
+static int slab_layers(const cf_sim* s, double w) {
+    int nxl = std::max(1, std::min((int)floor(w / s->cell_edge), 1022));
+    while (nxl > 1 && w / nxl < (double)s->rmax * (1.0 + 4.0 * nxl * 1.1920929e-7)) nxl--;
+    return nxl;
+}
 static float slab_bound(const cf_sim* s, int r);
+static float slab_width(const cf_sim* s, int r);
+static void slab_update_geom(cf_sim* s);
 
 // Chooses the cell grid for the current parameters and uploads the tables.
 static int prepare_step_const(cf_sim* s) {
@@ -399,8 +410,12 @@ static int prepare_step_const(cf_sim* s) {
     float W[3] = {p.canvasWidth, p.canvasHeight, p.canvasDepth};
     // cell edge >= R_max (1e-5 margin covers the rounding of pos * inv), and coarse enough that
     // the grid has at most opt_max_cells_per_particle * n cells
+    // Slab mode: the grid must be the same on every rank (ghost layers arrive sorted by the sender's cells, and
+    // both ends of a link size their messages from it), so it is derived from rank-invariant numbers only —
+    // the global count (or the capacity, equal on all ranks by contract), never this rank's own count.
     double vol = (double)W[0] * W[1] * W[2] / (s->slab ? s->world : 1);
-    double max_cells = std::max(64.0, s->opt_max_cells_per_particle * (double)std::max(s->n, 1));
+    double n_ref = s->slab ? (s->n_total > 0 ? (double)s->n_total / s->world : (double)s->cap_own) : (double)s->n;
+    double max_cells = std::max(64.0, s->opt_max_cells_per_particle * std::max(n_ref, 1.0));
     max_cells = std::min(max_cells, 16777216.0); // class * ncell * 64 must fit the 32-bit sort key
     double edge = std::max((double)rmax * (1.0 + 1e-5), cbrt(vol / max_cells));
     if (!(edge > 0.0)) edge = cbrt(vol / max_cells);
@@ -408,6 +423,10 @@ static int prepare_step_const(cf_sim* s) {
     for (int a = 0; a < 3; a++) {
         int d = (int)floor((double)W[a] / edge);
         d = std::max(1, std::min(d, 1024));
+        // the cell coordinate is fl(x * inv): its rounding error grows with the cell index (~d * 2^-24 cell
+        // widths), so the slack over R_max must grow with the grid too, or a pair just inside the cut-off
+        // could land two cells apart
+        while (d > 1 && (double)W[a] / d < (double)rmax * (1.0 + 4.0 * d * 1.1920929e-7)) d--;
         c.dims[a] = d;
         c.W[a] = W[a];
         c.halfW[a] = W[a] * 0.5f;
@@ -424,13 +443,12 @@ static int prepare_step_const(cf_sim* s) {
     c.gx_hi = c.dims[0] - 1;
     if (s->slab) {
         // owned x layers over the slab, one ghost layer on each side
-        s->geom.x_lo = slab_bound(s, s->rank);
-        s->geom.x_hi = slab_bound(s, s->rank + 1);
-        s->geom.W = W[0];
-        s->geom.slab_w = W[0] / (float)s->world;
-        double slab_w = (double)W[0] / s->world;
+        slab_update_geom(s);
+        double slab_w = (double)s->geom.x_hi - (double)s->geom.x_lo;
         ncell /= c.dims[0];
-        int nxl = std::max(1, std::min((int)floor(slab_w / edge), 1022));
+        s->cell_edge = edge;
+        s->rmax = rmax;
+        int nxl = slab_layers(s, slab_w);
         s->nxl = nxl;
         c.dims[0] = nxl + 2;
         c.inv[0] = (float)nxl / (s->geom.x_hi - s->geom.x_lo);
@@ -443,8 +461,11 @@ static int prepare_step_const(cf_sim* s) {
         c.gx_lo = s->rank == 0 ? 1 : 0;
         c.gx_hi = s->rank == s->world - 1 ? nxl : nxl + 1;
         ncell *= c.dims[0];
-        if ((double)rmax * (1.0 + 1e-5) > slab_w)
-            return fail(CF_ERR_ARG, "interaction radius %.1f exceeds the slab width %.1f: use fewer GPUs", rmax, slab_w);
+        // every slab (not only mine) must be at least one interaction radius wide: a ghost layer is one layer
+        for (int r = 0; r < s->world; r++)
+            if ((double)rmax * (1.0 + 1e-5) > (double)slab_width(s, r))
+                return fail(CF_ERR_ARG, "interaction radius %.1f exceeds the width %.1f of slab %d: use fewer GPUs", rmax,
+                            slab_width(s, r), r);
     }
     c.T = s->T;
     c.repulsion = p.repulsion;
@@ -550,8 +571,8 @@ static int ensure_sorted(cf_sim* s) {
 
 #include "slab_host.inl"
 
-static int build_cell_list(cf_sim* s, cudaEvent_t ev_x0 = nullptr, cudaEvent_t ev_x1 = nullptr) {
-    return s->slab ? ensure_sorted_slab(s, ev_x0, ev_x1) : ensure_sorted(s);
+static int build_cell_list(cf_sim* s, cudaEvent_t* ev_x = nullptr) {
+    return s->slab ? ensure_sorted_slab(s, ev_x) : ensure_sorted(s);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -644,13 +665,6 @@ extern "C" int cf_destroy(cf_sim* s) {
         if (g.exec) cudaGraphExecDestroy(g.exec);
     for (auto& g : s->graph_graphs)
         if (g.exec) cudaGraphExecDestroy(g.exec);
-    if (s->slab && getenv("CF_SLAB_DEBUG") && g_slab_times.calls > 5) {
-        double c = (double)(g_slab_times.calls - 5);
-        fprintf(stderr, "[cellflow_b200 rank %d] slab build x%lld: host total %.3f ms (wait own sort %.3f, wait migrants %.3f); "
-                        "device: migrant exchange %.3f ms, merge+reorder+bounds %.3f ms, halo exchange %.3f ms\n",
-                s->rank, g_slab_times.calls, 1e3 * g_slab_times.enqueue / c, 0.0,
-                1e3 * g_slab_times.mig_sync / c, g_slab_times.gpu_mig / c, g_slab_times.gpu_mid / c, g_slab_times.gpu_halo / c);
-    }
     slab_free(s);
     free_particle_buffers(s);
     cudaFree(s->hist);
@@ -676,7 +690,7 @@ extern "C" int cf_destroy(cf_sim* s) {
     cudaFree(s->h_comp);
     cudaFree(s->h_start);
     for (auto& ev : s->ev_pool)
-        for (int i = 0; i < 6; i++) cudaEventDestroy(ev.e[i]);
+        for (int i = 0; i < CF_STEP_EVENTS; i++) cudaEventDestroy(ev.e[i]);
     if (s->ev_g0) cudaEventDestroy(s->ev_g0);
     if (s->ev_g1) cudaEventDestroy(s->ev_g1);
     if (s->stream) cudaStreamDestroy(s->stream);
@@ -684,7 +698,16 @@ extern "C" int cf_destroy(cf_sim* s) {
     return CF_OK;
 }
 
-extern "C" int cf_get_particle_count(const cf_sim* s) { return s ? s->n : CF_ERR_ARG; }
+static int slab_refresh(cf_sim* s);
+extern "C" int cf_get_particle_count(const cf_sim* s) {
+    if (!s) return CF_ERR_ARG;
+    if (s->slab) { // the owned count lives on the device
+        cf_sim* m = const_cast<cf_sim*>(s);
+        if (cudaSetDevice(m->device) != cudaSuccess) return CF_ERR_CUDA;
+        if (int rc = slab_refresh(m)) return rc;
+    }
+    return s->n;
+}
 extern "C" int cf_get_num_particle_types(const cf_sim* s) { return s ? s->T : CF_ERR_ARG; }
 
 // setParticleCount (.cu:564-572): reallocate and re-spawn when the count changes.
@@ -811,6 +834,8 @@ static int upload_impl(cf_sim* s, const cf_particle* aos, const int32_t* counts,
     if (int rc = set_device(s)) return rc;
     if (s->slab) {
         if (count > s->cap_own) return fail(CF_ERR_CAPACITY, "%d particles exceed the rank capacity %d", count, s->cap_own);
+        if (int rc = slab_drain(s)) return rc; // collective, like the upload itself
+        if (int rc = slab_set_owned_count(s, count)) return rc;
     } else if (count > s->cap) {
         CU(cudaStreamSynchronize(s->stream));
         if (int rc = alloc_particle_buffers(s, count)) return rc;
@@ -845,8 +870,10 @@ extern "C" int cf_upload_particles_ids(cf_sim* s, const cf_particle* aos, const 
 }
 
 extern "C" int cf_download_particles(cf_sim* s, cf_particle* aos, int count) {
-    ARG(s && aos && count == s->n);
+    ARG(s && aos);
     if (int rc = set_device(s)) return rc;
+    if (int rc = slab_refresh(s)) return rc;
+    ARG(count == s->n);
     if (count == 0) return CF_OK;
     LAUNCH(s, soa_to_aos_kernel, div_up(count, 256), 256, 0, opos(s), ovel(s), ofrc(s),
            oid(s), s->d_aos, s->d_counts, count, 1);
@@ -858,6 +885,8 @@ extern "C" int cf_download_particles(cf_sim* s, cf_particle* aos, int count) {
 extern "C" int cf_download_particles_ids(cf_sim* s, cf_particle* aos, int32_t* counts, int32_t* ids,
                                          int capacity, int* count) {
     ARG(s && count);
+    if (int rc = set_device(s)) return rc;
+    if (int rc = slab_refresh(s)) return rc; // slab mode: the owned count lives on the device
     *count = s->n;
     ARG(capacity >= s->n);
     if (int rc = set_device(s)) return rc;
@@ -872,8 +901,10 @@ extern "C" int cf_download_particles_ids(cf_sim* s, cf_particle* aos, int32_t* c
 }
 
 extern "C" int cf_upload_neighbor_counts(cf_sim* s, const int32_t* counts, int count) {
-    ARG(s && counts && count == s->n);
+    ARG(s && counts);
     if (int rc = set_device(s)) return rc;
+    if (int rc = slab_refresh(s)) return rc;
+    ARG(count == s->n);
     if (count == 0) return CF_OK;
     CU(cudaMemcpyAsync(s->d_counts, counts, sizeof(int) * (size_t)count, cudaMemcpyHostToDevice, s->stream));
     LAUNCH(s, scatter_counts_kernel, div_up(count, 256), 256, 0, s->d_counts, oid(s), ovel(s), count);
@@ -882,8 +913,10 @@ extern "C" int cf_upload_neighbor_counts(cf_sim* s, const int32_t* counts, int c
 }
 
 extern "C" int cf_download_neighbor_counts(cf_sim* s, int32_t* counts, int count) {
-    ARG(s && counts && count == s->n);
+    ARG(s && counts);
     if (int rc = set_device(s)) return rc;
+    if (int rc = slab_refresh(s)) return rc;
+    ARG(count == s->n);
     if (count == 0) return CF_OK;
     LAUNCH(s, soa_to_aos_kernel, div_up(count, 256), 256, 0, opos(s), ovel(s), ofrc(s),
            oid(s), s->d_aos, s->d_counts, count, 1);
@@ -894,8 +927,9 @@ extern "C" int cf_download_neighbor_counts(cf_sim* s, int32_t* counts, int count
 
 extern "C" int cf_render_feed(cf_sim* s, float* xyzt, int capacity, int32_t* type_counts, const void** device_ptr) {
     ARG(s);
-    ARG(xyzt == nullptr || capacity >= s->n);
     if (int rc = set_device(s)) return rc;
+    if (int rc = slab_refresh(s)) return rc;
+    ARG(xyzt == nullptr || capacity >= s->n);
     if (device_ptr) *device_ptr = nullptr;
     if (s->n == 0) {
         if (type_counts) memset(type_counts, 0, sizeof(int32_t) * s->T);
@@ -915,6 +949,10 @@ extern "C" int cf_render_feed(cf_sim* s, float* xyzt, int capacity, int32_t* typ
 extern "C" int cf_move_universe(cf_sim* s, float dx, float dy, float dz) {
     ARG(s);
     if (int rc = set_device(s)) return rc;
+    if (s->slab) { // consume a pending migrant exchange first; the shift may move particles across a face
+        if (int rc = slab_drain(s)) return rc;
+        if (int rc = slab_refresh(s)) return rc;
+    }
     if (s->n == 0) return CF_OK;
     // the reference passes the DEFAULT canvas here (.cu:586-589); the engine uses the live one
     LAUNCH(s, move_universe_kernel, div_up(s->n, 256), 256, 0, opos(s), s->n, dx, dy, dz,
@@ -953,7 +991,7 @@ static StepEvents* next_events(cf_sim* s) {
     if (s->ev_used == s->ev_pool.size()) {
         if (s->ev_pool.size() >= 4096) return nullptr;
         StepEvents ev;
-        for (int i = 0; i < 6; i++)
+        for (int i = 0; i < CF_STEP_EVENTS; i++)
             if (cudaEventCreate(&ev.e[i]) != cudaSuccess) return nullptr;
         s->ev_pool.push_back(ev);
     }
@@ -965,7 +1003,10 @@ static StepEvents* next_events(cf_sim* s) {
 static int build_homog_copy(cf_sim* s) {
     const int nz = s->sc.dims[2];
     const int nrow = s->ncell / nz;
-    const int nslots = s->slab ? std::min(s->cap, s->base + s->n + s->cap_halo) : s->n;
+    // slab mode: every slot up to the end of the right ghost layer, a count only the device knows
+    // (cell_start[ncell]); slots before the left ghost layer hold nothing and get the sentinel key
+    const int nslots = s->slab ? s->cap : s->n;
+    const int* d_nslots = s->slab ? s->cell_start + s->ncell : nullptr;
     const int nkeys = nrow * s->T * nz; // composite keys (row * T + type) * nz + cz
     if ((size_t)nslots > s->homog_cap) {
         CU(cudaStreamSynchronize(s->stream));
@@ -995,13 +1036,13 @@ static int build_homog_copy(cf_sim* s) {
         CU(cudaMalloc(&s->h_start, s->h_start_cap * sizeof(int)));
     }
     const float4* pos = s->pos[s->cur];
-    LAUNCH(s, homog_key_kernel, div_up(nslots, 256), 256, 0, pos, s->cell_start, s->ncell, nz, s->T, nslots, s->hk[0],
-           s->hv[0], s->h_cell_of);
+    LAUNCH(s, homog_key_kernel, div_up(nslots, 256), 256, 0, pos, s->cell_start, s->ncell, nz, s->T, nslots, d_nslots,
+           s->hk[0], s->hv[0], s->h_cell_of);
     int src = 0;
-    if (int rc = radix_sort_pairs(s, s->hk, s->hv, nslots, (long long)nrow * s->T + 1, &src)) return rc;
+    if (int rc = radix_sort_pairs(s, s->hk, s->hv, nslots, (long long)nrow * s->T + 1, &src, d_nslots)) return rc;
     LAUNCH(s, homog_gather_kernel, div_up(nslots, 256), 256, 0, s->hk[src], s->hv[src], pos, s->h_cell_of, nz, nslots,
-           s->h_pos, s->h_comp);
-    LAUNCH(s, homog_bounds_kernel, div_up(nkeys + 1, 256), 256, 0, s->h_comp, nslots, s->h_start, nkeys);
+           d_nslots, s->h_pos, s->h_comp);
+    LAUNCH(s, homog_bounds_kernel, div_up(nkeys + 1, 256), 256, 0, s->h_comp, nslots, d_nslots, s->h_start, nkeys);
     return 0;
 }
 
@@ -1045,7 +1086,7 @@ static int launch_force(cf_sim* s) {
            s->d_cell_occ, s->h_cell_occ);
     s->last_force_kernel = kernel;
     if (kernel == 2 || kernel == 3) {
-        size_t need = (size_t)s->ncell + (size_t)n / TK_TI + 2;
+        size_t need = (size_t)s->ncell + (size_t)(s->slab ? s->cap_own : n) / TK_TI + 2;
         if (need > s->tiles_cap) {
             CU(cudaStreamSynchronize(s->stream));
             cudaFree(s->d_tiles);
@@ -1086,10 +1127,12 @@ static int launch_force(cf_sim* s) {
                    s->frc, s->sc, s->d_tables, 0.f, s->d_half);
         return 0;
     }
+    const int nu = s->slab ? s->cap_own : n; // slab mode: the owned count is read on the device
+    const int* dn = s->slab ? s->d_slab + SLAB_NCUR : nullptr;
     if (s->sc.uniform_radius)
-        LAUNCH(s, force_pp_kernel<true>, div_up(n, 128), 128, 0, pos, s->cell_start, s->frc, s->base, n, s->sc, s->d_tables);
+        LAUNCH(s, force_pp_kernel<true>, div_up(nu, 128), 128, 0, pos, s->cell_start, s->frc, s->base, nu, dn, s->sc, s->d_tables);
     else
-        LAUNCH(s, force_pp_kernel<false>, div_up(n, 128), 128, 0, pos, s->cell_start, s->frc, s->base, n, s->sc, s->d_tables);
+        LAUNCH(s, force_pp_kernel<false>, div_up(nu, 128), 128, 0, pos, s->cell_start, s->frc, s->base, nu, dn, s->sc, s->d_tables);
     return 0;
 }
 
@@ -1098,12 +1141,20 @@ static int launch_force(cf_sim* s) {
 static int step_direct(cf_sim* s, StepEvents* ev) {
     if (ev) CU(cudaEventRecord(ev->e[0], s->stream));
     if (ev) ev->has_exchange = s->slab && !s->sorted_valid;
-    if (int rc = build_cell_list(s, ev ? ev->e[4] : nullptr, ev ? ev->e[5] : nullptr)) return rc;
+    if (int rc = build_cell_list(s, ev ? &ev->e[4] : nullptr)) return rc;
     if (ev) CU(cudaEventRecord(ev->e[1], s->stream));
-    if (s->n > 0)
+    if (s->n > 0 || s->slab)
         if (int rc = launch_force(s)) return rc;
     if (ev) CU(cudaEventRecord(ev->e[2], s->stream));
-    if (s->n > 0) LAUNCH(s, integrate_kernel, div_up(s->n, 256), 256, 0, opos(s), ovel(s), ofrc(s), s->n, s->sc);
+    if (s->slab) {
+        // fused integrate + migrant emission: the leavers go straight into the neighbours' mailboxes
+        s->seq_mig++;
+        LAUNCH(s, integrate_slab_kernel, div_up(s->cap_own, 256), 256, 0, opos(s), ovel(s), ofrc(s), oid(s), s->cap_own, s->sc,
+               s->geom, slab_peers(s), s->seq_mig);
+        s->mig_sent = true;
+    } else if (s->n > 0) {
+        LAUNCH(s, integrate_kernel, div_up(s->n, 256), 256, 0, opos(s), ovel(s), ofrc(s), s->n, s->sc);
+    }
     if (ev) CU(cudaEventRecord(ev->e[3], s->stream));
     s->sorted_valid = false;
     return 0;
@@ -1220,6 +1271,7 @@ extern "C" int cf_sync(cf_sim* s) {
     if (int rc = set_device(s)) return rc;
     CU(cudaStreamSynchronize(s->stream));
     refresh_policy(s);
+    if (int rc = slab_refresh(s)) return rc; // slab mode: owned count + the device-side error word
     return CF_OK;
 }
 
@@ -1271,22 +1323,29 @@ static int graph_make_plan(cf_sim* s, float dist, int mc, GraphPlan& P) {
     float ext_lo[3] = {0.f, 0.f, 0.f};
     float ext_hi[3] = {s->sc.W[0], s->sc.W[1], s->sc.W[2]};
     if (s->slab) {
-        float ex = (s->sc.W[0] / (float)s->world) / (float)s->nxl;
-        if ((double)dist * (1.0 + 1e-5) > (double)ex)
-            return fail(CF_ERR_ARG, "proximity distance %.1f exceeds the one-cell ghost layer (%.1f) of slab mode", dist, ex);
-        // every slot that can hold a particle; the key kernel reads the ghost extents on the device
+        // a ghost layer is one x layer of the neighbour: the graph may not reach further than the thinnest of them
+        float ex_left = 0.f, ex_right = 0.f, ex_min = INFINITY;
+        for (int r = 0; r < s->world; r++) {
+            const double w = slab_width(s, r);
+            const float exr = (float)(w / slab_layers(s, w));
+            ex_min = std::min(ex_min, exr);
+            if (r == (s->rank + s->world - 1) % s->world) ex_left = exr;
+            if (r == (s->rank + 1) % s->world) ex_right = exr;
+        }
+        if ((double)dist * (1.0 + 1e-5) > (double)ex_min)
+            return fail(CF_ERR_ARG, "proximity distance %.1f exceeds the one-cell ghost layer (%.1f) of slab mode", dist, ex_min);
+        // every slot that can hold a particle; the key kernel reads the real extents on the device
         P.use_lo_ghost = s->rank > 0, P.use_hi_ghost = s->rank < s->world - 1;
-        P.first = P.use_lo_ghost ? std::max(0, s->base - slab_halo_msg_cap(s)) : s->base;
-        int last = std::min(s->cap, s->base + s->n + (P.use_hi_ghost ? slab_halo_msg_cap(s) : 0));
-        P.count = last - P.first;
-        ext_lo[0] = s->geom.x_lo - ex;
-        ext_hi[0] = s->geom.x_hi + ex;
+        P.first = 0;
+        P.count = s->cap;
+        ext_lo[0] = s->geom.x_lo - ex_left;
+        ext_hi[0] = s->geom.x_hi + ex_right;
     }
     // ---- the graph's own (type, cell) list, cell edge >= dist ----
     GraphGrid& g = P.g;
     double edge = (double)dist * (1.0 + 1e-5), vol = 1.0;
     for (int a = 0; a < 3; a++) vol *= (double)(ext_hi[a] - ext_lo[a]);
-    double max_keys = std::min(4.0 * std::max(P.count, 0) + 4096.0, 1.6e7);
+    double max_keys = std::min(4.0 * std::max(s->slab ? s->cap_own : P.count, 0) + 4096.0, 1.6e7);
     edge = std::max(edge, cbrt(vol * s->T / max_keys));
     long long nc = 1;
     for (int a = 0; a < 3; a++) {
@@ -1347,23 +1406,26 @@ static int graph_device_sequence(cf_sim* s, const GraphPlan& P, bool with_cell_l
         if (int rc = build_cell_list(s)) return rc;
     CU(cudaMemsetAsync(s->d_edge_count, 0, sizeof(int), s->stream));
     CU(cudaMemsetAsync(s->d_graph_occ, 0, sizeof(unsigned long long), s->stream));
-    if (!(P.count > 0 && s->n > 0)) return 0;
+    if (!(P.count > 0 && (s->n > 0 || s->slab))) return 0;
     const int count = P.count, nkeys = P.nkeys;
-    LAUNCH(s, graph_key_kernel, div_up(count, 256), 256, 0, s->pos[s->cur], P.first, count, P.g, s->cell_start, s->ncell,
-           s->base, s->n, P.use_lo_ghost, P.use_hi_ghost, s->gk[0], s->gv[0]);
+    // slab mode: slots [0, cell_start[ncell]) take part and the owned count is a device word
+    const int* d_n = s->slab ? s->cell_start + s->ncell : nullptr;
+    const int* d_own = s->slab ? s->d_slab + SLAB_NCUR : nullptr;
+    LAUNCH(s, graph_key_kernel, div_up(count, 256), 256, 0, s->pos[s->cur], P.first, count, d_n, P.g, s->cell_start, s->ncell,
+           s->base, s->n, d_own, P.use_lo_ghost, P.use_hi_ghost, s->gk[0], s->gv[0]);
     int src = 0;
-    if (int rc = radix_sort_pairs(s, s->gk, s->gv, count, (long long)nkeys + 1, &src)) return rc;
-    LAUNCH(s, graph_gather_kernel, div_up(count, 256), 256, 0, s->gv[src], s->pos[s->cur], s->id[s->cur], count, s->gpos);
-    LAUNCH(s, graph_bounds_kernel, div_up(nkeys + 1, 256), 256, 0, s->gk[src], count, s->gstart, nkeys);
+    if (int rc = radix_sort_pairs(s, s->gk, s->gv, count, (long long)nkeys + 1, &src, d_n)) return rc;
+    LAUNCH(s, graph_gather_kernel, div_up(count, 256), 256, 0, s->gv[src], s->pos[s->cur], s->id[s->cur], count, d_n, s->gpos);
+    LAUNCH(s, graph_bounds_kernel, div_up(nkeys + 1, 256), 256, 0, s->gk[src], count, d_n, s->gstart, nkeys);
     LAUNCH(s, graph_occupancy_kernel, div_up(nkeys, 256), 256, 0, s->gstart, nkeys, s->d_graph_occ);
     if (P.gkernel == 2)
         LAUNCH(s, graph_warp_kernel, div_up(count, CF_GRAPHW_WARPS), CF_GRAPHW_WARPS * 32, 0, s->gpos, s->gv[src],
-               s->gk[src], s->gstart, count, s->base, s->n, P.g, P.dist2, P.mc, s->edges, s->edge_slots, s->edge_cap,
-               s->d_edge_count);
+               s->gk[src], s->gstart, count, d_n, s->base, s->n, d_own, P.g, P.dist2, P.mc, s->edges, s->edge_slots,
+               s->edge_cap, s->d_edge_count);
     else
         LAUNCH(s, graph_kernel, div_up(count, CF_GRAPH_THREADS), CF_GRAPH_THREADS,
-               (size_t)3 * 2 * P.mc * CF_GRAPH_THREADS * sizeof(int), s->gpos, s->gv[src], s->gk[src], s->gstart, count,
-               s->base, s->n, P.g, P.dist2, P.mc, s->edges, s->edge_slots, s->edge_cap, s->d_edge_count);
+               (size_t)3 * 2 * P.mc * CF_GRAPH_THREADS * sizeof(int), s->gpos, s->gv[src], s->gk[src], s->gstart, count, d_n,
+               s->base, s->n, d_own, P.g, P.dist2, P.mc, s->edges, s->edge_slots, s->edge_cap, s->d_edge_count);
     return 0;
 }
 
@@ -1547,10 +1609,9 @@ extern "C" int cf_set_option(cf_sim* s, const char* name, double value) {
     else if (k == "max_cells_per_particle") s->opt_max_cells_per_particle = value;
     else if (k == "cuda_graphs") s->opt_graphs = (int)value;
     else if (k == "global_particle_count") s->n_total = (long long)value; // same value on every rank
-    else if (k == "halo_slack") s->halo_slack = value;
-    else if (k == "migrant_slack") s->mig_slack = value;
-    else if (k == "halo_capacity") s->cap_halo = (int)value;       // before cf_comm_init
-    else if (k == "migrant_capacity") s->cap_mig = (int)value;     // before cf_comm_init
+    else if (k == "halo_capacity") s->cap_halo = (int)value;       // before cf_comm_init, same on every rank
+    else if (k == "migrant_capacity") s->cap_mig = (int)value;     // before cf_comm_init, same on every rank
+    else if (k == "wait_timeout_ms") s->wait_timeout_ms = value;
     else return fail(CF_ERR_ARG, "unknown option '%s'", name);
     s->sorted_valid = false;
     return CF_OK;
@@ -1574,6 +1635,7 @@ extern "C" int cf_get_stats(cf_sim* s, cf_stats* st) {
     ARG(s && st);
     if (int rc = set_device(s)) return rc;
     CU(cudaStreamSynchronize(s->stream));
+    const int slab_rc = slab_refresh(s); // slab mode: owned count + error word (reported after the numbers are filled in)
     for (size_t i = 0; i < s->ev_used; i++) {
         float a = 0, b = 0, c = 0;
         StepEvents& ev = s->ev_pool[i];
@@ -1583,9 +1645,11 @@ extern "C" int cf_get_stats(cf_sim* s, cf_stats* st) {
         s->ms_sort += a;
         s->ms_force += b;
         s->ms_integrate += c;
-        if (ev.has_exchange) {
-            float x = 0;
-            if (cudaEventElapsedTime(&x, ev.e[4], ev.e[5]) == cudaSuccess) s->ms_exchange += x;
+        if (ev.has_exchange) { // the two mailbox exchanges: wait + append arrivals, halo pack + wait + ghosts
+            float x = 0, y = 0;
+            if (cudaEventElapsedTime(&x, ev.e[4], ev.e[5]) == cudaSuccess &&
+                cudaEventElapsedTime(&y, ev.e[6], ev.e[7]) == cudaSuccess)
+                s->ms_exchange += x + y;
         }
         s->ms_total += a + b + c;
         s->stat_steps++;
@@ -1609,15 +1673,11 @@ extern "C" int cf_get_stats(cf_sim* s, cf_stats* st) {
     st->graph_kernel = s->last_graph_kernel;
     st->ms_graph_total = s->ms_graph_total;
     st->graph_builds = s->graph_builds;
-    if (s->slab) {
-        int g[2] = {0, 0};
-        CU(cudaMemcpy(g, s->d_slab_counts + 4, 2 * sizeof(int), cudaMemcpyDeviceToHost));
-        st->n_ghost = g[0] + g[1];
-    }
+    if (s->slab) st->n_ghost = s->h_slab[SLAB_GHOST_L] + s->h_slab[SLAB_GHOST_R];
     if (s->n > 0) {
         unsigned long long acc = 0;
         CU(cudaMemsetAsync(s->d_accum, 0, sizeof(unsigned long long), s->stream));
-        sum_counts_kernel<<<148 * 4, 256, 0, s->stream>>>(ofrc(s), s->n, s->d_accum);
+        sum_counts_kernel<<<s->sm_count * 4, 256, 0, s->stream>>>(ofrc(s), s->n, s->d_accum);
         CU(cudaMemcpyAsync(&acc, s->d_accum, sizeof(acc), cudaMemcpyDeviceToHost, s->stream));
         CU(cudaStreamSynchronize(s->stream));
         st->accepted_pairs = (long long)acc;
@@ -1631,6 +1691,7 @@ extern "C" int cf_get_stats(cf_sim* s, cf_stats* st) {
             st->tested_pairs = (long long)acc;
         }
     }
+    if (slab_rc) return slab_rc;
     return CF_OK;
 }
 

@@ -35,7 +35,7 @@ __device__ __forceinline__ int cf_axis_cells(int c, int n, bool periodic, int ou
 template <bool UNIFORM>
 __global__ void __launch_bounds__(128)
 force_pp_kernel(const float4* __restrict__ pos4, const int* __restrict__ cell_start,
-                float4* __restrict__ frc4, int first, int n, StepConst c,
+                float4* __restrict__ frc4, int first, int n_upper, const int* __restrict__ dn, StepConst c,
                 const DeviceTables* __restrict__ tables) {
     __shared__ float s_cut2[CF_TT_MAX], s_inv[CF_TT_MAX], s_fv[CF_TT_MAX];
     for (int i = threadIdx.x; i < c.T * c.T; i += blockDim.x) {
@@ -44,6 +44,7 @@ force_pp_kernel(const float4* __restrict__ pos4, const int* __restrict__ cell_st
         s_fv[i] = tables->force[i];
     }
     __syncthreads();
+    const int n = dn ? min(*dn, n_upper) : n_upper; // slab mode: the owned count lives on the device
     int s = first + blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= first + n) return;
     float4 p = pos4[s];

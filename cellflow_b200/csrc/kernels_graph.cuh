@@ -36,10 +36,13 @@ __device__ __forceinline__ int graph_coord(float x, float org, float inv, int n)
 // the low / high ghost layer when it is a real neighbour (not the periodic seam).  The ghost
 // extents are read from the cell list on the device (cell_start[0], cell_start[ncell]), so the
 // host never has to wait for the ghost counts.
-__global__ void graph_key_kernel(const float4* __restrict__ pos4, int first, int n, GraphGrid g,
-                                 const int* __restrict__ cell_start, int ncell, int own_first, int own_n,
-                                 int use_lo_ghost, int use_hi_ghost, uint32_t* __restrict__ keys,
-                                 uint32_t* __restrict__ vals) {
+// Slab mode: the slot count (d_n) and the owned count (d_own_n) are read on the device.
+__global__ void graph_key_kernel(const float4* __restrict__ pos4, int first, int n_upper, const int* __restrict__ d_n,
+                                 GraphGrid g, const int* __restrict__ cell_start, int ncell, int own_first, int own_n_host,
+                                 const int* __restrict__ d_own_n, int use_lo_ghost, int use_hi_ghost,
+                                 uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+    const int n = d_n ? min(*d_n, n_upper) : n_upper;
+    const int own_n = d_own_n ? *d_own_n : own_n_host;
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     const int slot = first + k;
@@ -62,7 +65,9 @@ __global__ void graph_key_kernel(const float4* __restrict__ pos4, int first, int
 
 // Positions in graph order with the original id in .w, so the candidate loop is one 16-byte load.
 __global__ void graph_gather_kernel(const uint32_t* __restrict__ gvals, const float4* __restrict__ pos4,
-                                    const int* __restrict__ id, int n, float4* __restrict__ gpos) {
+                                    const int* __restrict__ id, int n_upper, const int* __restrict__ d_n,
+                                    float4* __restrict__ gpos) {
+    const int n = d_n ? min(*d_n, n_upper) : n_upper;
     int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= n) return;
     uint32_t slot = gvals[q];
@@ -71,7 +76,9 @@ __global__ void graph_gather_kernel(const uint32_t* __restrict__ gvals, const fl
 }
 
 // gstart[k] = first graph-order position whose key is >= k, k in [0, nkeys].
-__global__ void graph_bounds_kernel(const uint32_t* __restrict__ skeys, int n, int* __restrict__ gstart, int nkeys) {
+__global__ void graph_bounds_kernel(const uint32_t* __restrict__ skeys, int n_upper, const int* __restrict__ d_n,
+                                    int* __restrict__ gstart, int nkeys) {
+    const int n = d_n ? min(*d_n, n_upper) : n_upper;
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k > nkeys) return;
     int lo = 0, hi = n;
@@ -104,10 +111,12 @@ struct GraphList {
 
 __global__ void __launch_bounds__(CF_GRAPH_THREADS)
 graph_kernel(const float4* __restrict__ gpos, const uint32_t* __restrict__ gvals, const uint32_t* __restrict__ gkeys,
-             const int* __restrict__ gstart, int nq, int own_first, int n_own, GraphGrid g, float dist2,
-             int max_conn, int2* __restrict__ edges, int2* __restrict__ edge_slots, int capacity,
-             int* __restrict__ edge_count) {
-    extern __shared__ int s_lists[]; // [3][K][CF_GRAPH_THREADS]: id, graph position, d2
+             const int* __restrict__ gstart, int nq_upper, const int* __restrict__ d_nq, int own_first, int n_own_host,
+             const int* __restrict__ d_own_n, GraphGrid g, float dist2, int max_conn, int2* __restrict__ edges,
+             int2* __restrict__ edge_slots, int capacity, int* __restrict__ edge_count) {
+    extern __shared__ int s_lists[];
+    const int nq = d_nq ? min(*d_nq, nq_upper) : nq_upper;
+    const int n_own = d_own_n ? *d_own_n : n_own_host; // [3][K][CF_GRAPH_THREADS]: id, graph position, d2
     const int K = 2 * max_conn;
     GraphList L{s_lists + threadIdx.x, s_lists + K * CF_GRAPH_THREADS + threadIdx.x,
                 reinterpret_cast<float*>(s_lists + 2 * K * CF_GRAPH_THREADS) + threadIdx.x};
@@ -215,9 +224,11 @@ graph_kernel(const float4* __restrict__ gpos, const uint32_t* __restrict__ gvals
 #define CF_GRAPHW_WARPS 4
 __global__ void __launch_bounds__(CF_GRAPHW_WARPS * 32)
 graph_warp_kernel(const float4* __restrict__ gpos, const uint32_t* __restrict__ gvals, const uint32_t* __restrict__ gkeys,
-                  const int* __restrict__ gstart, int nq, int own_first, int n_own, GraphGrid g, float dist2,
-                  int max_conn, int2* __restrict__ edges, int2* __restrict__ edge_slots, int capacity,
-                  int* __restrict__ edge_count) {
+                  const int* __restrict__ gstart, int nq_upper, const int* __restrict__ d_nq, int own_first,
+                  int n_own_host, const int* __restrict__ d_own_n, GraphGrid g, float dist2, int max_conn,
+                  int2* __restrict__ edges, int2* __restrict__ edge_slots, int capacity, int* __restrict__ edge_count) {
+    const int nq = d_nq ? min(*d_nq, nq_upper) : nq_upper;
+    const int n_own = d_own_n ? *d_own_n : n_own_host;
     const int lane = threadIdx.x & 31;
     const int q = blockIdx.x * CF_GRAPHW_WARPS + (threadIdx.x >> 5); // warp-uniform
     if (q >= nq) return;

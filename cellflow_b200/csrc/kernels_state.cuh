@@ -164,11 +164,7 @@ __global__ void fill_int_kernel(int* __restrict__ a, int n, int v) {
 //   a = fma(dens, -(1 - balance), 1);   m = a * forceMultiplier;   acc = m * F
 //   vel = fma(vel, friction, acc * dt);  pos = fma(vel, dt, pos);  pos = fmodf(pos + W, W)
 // HBM traffic: reads pos 16 + vel 16 + frc 16, writes pos 16 + vel 16 + frc 16 = 96 B/particle.
-__global__ void integrate_kernel(float4* __restrict__ pos4, float4* __restrict__ vel4,
-                                 float4* __restrict__ frc4, int n, StepConst c) {
-    int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
-    float4 p = pos4[k], v = vel4[k], f = frc4[k];
+__device__ __forceinline__ void cf_integrate_particle(float4& p, float4& v, float4& f, const StepConst& c) {
     int count = __float_as_int(f.w);
     int prev = __float_as_int(v.w);
     float avg = __fmul_rn((float)(count + prev), 0.5f);
@@ -183,9 +179,18 @@ __global__ void integrate_kernel(float4* __restrict__ pos4, float4* __restrict__
     p.y = fmodf(__fadd_rn(__fmaf_rn(v.y, c.dt, p.y), c.W[1]), c.W[1]);
     p.z = fmodf(__fadd_rn(__fmaf_rn(v.z, c.dt, p.z), c.W[2]), c.W[2]);
     v.w = __int_as_float(count);
+    f = make_float4(ax, ay, az, f.w);
+}
+
+__global__ void integrate_kernel(float4* __restrict__ pos4, float4* __restrict__ vel4,
+                                 float4* __restrict__ frc4, int n, StepConst c) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    float4 p = pos4[k], v = vel4[k], f = frc4[k];
+    cf_integrate_particle(p, v, f, c);
     pos4[k] = p;
     vel4[k] = v;
-    frc4[k] = make_float4(ax, ay, az, f.w);
+    frc4[k] = f;
 }
 
 // Render feed (CellFlowWidget::updateParticleBuffer, CellFlowWidget.cpp:742-761, and

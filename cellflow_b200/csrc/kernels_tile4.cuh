@@ -459,8 +459,9 @@ force_tile4_kernel(const float4* __restrict__ pos4, const int* __restrict__ cell
 // order already is (row, z cell, Morton)), a gather, and a lower-bound pass.
 // ---------------------------------------------------------------------------------------------
 __global__ void homog_key_kernel(const float4* __restrict__ pos4, const int* __restrict__ cell_start, int ncell,
-                                 int nz, int T, int nslots, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals,
-                                 int* __restrict__ cell_of) {
+                                 int nz, int T, int nslots_upper, const int* __restrict__ d_nslots,
+                                 uint32_t* __restrict__ keys, uint32_t* __restrict__ vals, int* __restrict__ cell_of) {
+    const int nslots = d_nslots ? min(*d_nslots, nslots_upper) : nslots_upper;
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= nslots) return;
     uint32_t key = (uint32_t)((ncell / nz) * T); // sentinel: slot holds no particle
@@ -483,7 +484,9 @@ __global__ void homog_key_kernel(const float4* __restrict__ pos4, const int* __r
 
 __global__ void homog_gather_kernel(const uint32_t* __restrict__ skeys, const uint32_t* __restrict__ svals,
                                     const float4* __restrict__ pos4, const int* __restrict__ cell_of, int nz,
-                                    int nslots, float4* __restrict__ posj, uint32_t* __restrict__ comp) {
+                                    int nslots_upper, const int* __restrict__ d_nslots, float4* __restrict__ posj,
+                                    uint32_t* __restrict__ comp) {
+    const int nslots = d_nslots ? min(*d_nslots, nslots_upper) : nslots_upper;
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= nslots) return;
     const uint32_t src = svals[k];
@@ -493,7 +496,9 @@ __global__ void homog_gather_kernel(const uint32_t* __restrict__ skeys, const ui
 }
 
 // startj[e] = first index of the sorted copy whose composite key (row*T + type)*nz + cz is >= e
-__global__ void homog_bounds_kernel(const uint32_t* __restrict__ comp, int nslots, int* __restrict__ startj, int nkeys) {
+__global__ void homog_bounds_kernel(const uint32_t* __restrict__ comp, int nslots_upper, const int* __restrict__ d_nslots,
+                                    int* __restrict__ startj, int nkeys) {
+    const int nslots = d_nslots ? min(*d_nslots, nslots_upper) : nslots_upper;
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e > nkeys) return;
     int lo = 0, hi = nslots;

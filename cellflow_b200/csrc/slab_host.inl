@@ -1,251 +1,225 @@
 // slab_host.inl — host side of the multi-GPU slab decomposition (included by engine.cu).
-// One process per GPU; ring neighbours exchange migrants and one ghost layer per step with
-// ncclSend/ncclRecv (or plain device copies when world == 1, which exercises the same code
-// path on a single GPU).
+// One process per GPU.  Ring neighbours exchange migrants and one ghost layer per step by storing into each
+// other's mailboxes (CUDA IPC mapped device memory, NVLink 5 / NVSwitch) from inside the producing kernels —
+// no NCCL call, no host synchronisation and no host-visible count anywhere on the step path (device side:
+// kernels_slab.cuh).  world == 1 maps the rank's own mailbox as both neighbours, which runs the identical
+// protocol on a single GPU.
 
 static void slab_free(cf_sim* s) {
     for (int d = 0; d < 2; d++) {
-        cudaFree(s->send_mig[d]);
-        cudaFree(s->recv_mig[d]);
-        cudaFree(s->send_halo[d]);
-        cudaFree(s->recv_halo[d]);
-        cudaFree(s->akeys[d]);
-        cudaFree(s->avals[d]);
+        if (s->peer_box[d] && s->peer_box[d] != s->mailbox && !(d == 1 && s->peer_box[1] == s->peer_box[0]))
+            cudaIpcCloseMemHandle(s->peer_box[d]);
         cudaFree(s->gkeys[d]);
-        s->send_mig[d] = s->recv_mig[d] = s->send_halo[d] = s->recv_halo[d] = nullptr;
-        s->akeys[d] = s->avals[d] = s->gkeys[d] = nullptr;
+        s->gkeys[d] = nullptr;
     }
-    cudaFree(s->d_slab_counts);
-    s->d_slab_counts = nullptr;
-    if (s->h_slab_counts) cudaFreeHost(s->h_slab_counts);
-    s->h_slab_counts = nullptr;
-    if (s->comm && nccl_api().ok) nccl_api().CommDestroy(s->comm);
-    s->comm = nullptr;
+    s->peer_box[0] = s->peer_box[1] = nullptr;
+    cudaFree(s->mailbox);
+    s->mailbox = nullptr;
+    cudaFree(s->d_slab);
+    s->d_slab = nullptr;
+    if (s->h_slab) cudaFreeHost(s->h_slab);
+    s->h_slab = nullptr;
+    s->connected = false;
 }
 
+// Slab bound r of `world`: the user's bounds (cf_slab_set_bounds, identical on every rank) or the uniform split.
 static float slab_bound(const cf_sim* s, int r) {
+    if (!s->bounds.empty()) return s->bounds[(size_t)std::max(0, std::min(r, s->world))];
     return (float)((double)s->params.canvasWidth * (double)r / (double)s->world);
 }
-
-#define NCCLCHK(call)                                                                         \
-    do {                                                                                      \
-        ncclResult_t r_ = (call);                                                             \
-        if (r_ != 0)                                                                          \
-            return fail(CF_ERR_NCCL, "%s failed: %s", #call, nccl_api().GetErrorString(r_)); \
-    } while (0)
-
-extern "C" int cf_nccl_unique_id(void* id128) {
-    ARG(id128);
-    NcclApi& api = nccl_api();
-    if (!api.ok) return fail(CF_ERR_NCCL, "NCCL unavailable: %s", api.why);
-    ncclUniqueId id;
-    NCCLCHK(api.GetUniqueId(&id));
-    memcpy(id128, &id, 128);
-    return CF_OK;
+static float slab_width(const cf_sim* s, int r) {
+    r = ((r % s->world) + s->world) % s->world;
+    return slab_bound(s, r + 1) - slab_bound(s, r);
 }
 
-extern "C" int cf_comm_init(cf_sim* s, int rank, int world, const void* id128, int capacity) {
+static void slab_update_geom(cf_sim* s) {
+    s->geom.x_lo = slab_bound(s, s->rank);
+    s->geom.x_hi = slab_bound(s, s->rank + 1);
+    s->geom.W = s->params.canvasWidth;
+    s->geom.w_own = slab_width(s, s->rank);
+    s->geom.w_left = slab_width(s, s->rank - 1);
+    s->geom.w_right = slab_width(s, s->rank + 1);
+}
+
+static SlabPeers slab_peers(const cf_sim* s) {
+    SlabPeers P;
+    P.left = s->peer_box[0];
+    P.right = s->peer_box[1];
+    P.mail = s->mail;
+    P.status = s->d_slab;
+    return P;
+}
+
+// The owned count and the error word live on the device; this is where the host learns them (called where
+// the API synchronises anyway: cf_sync, downloads, stats, graph results).
+static int slab_refresh(cf_sim* s) {
+    if (!s->slab) return 0;
+    CU(cudaMemcpyAsync(s->h_slab, s->d_slab, SLAB_WORDS * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    s->n = std::max(0, std::min(s->h_slab[SLAB_NCUR], s->cap_own));
+    const int e = s->h_slab[SLAB_ERR];
+    if (e == 0) return 0;
+    cudaMemsetAsync(s->d_slab + SLAB_ERR, 0, sizeof(int), s->stream); // reported once
+    if (e & SLAB_ERR_TIMEOUT)
+        return fail(CF_ERR_STATE, "rank %d: a neighbour's message did not arrive within %.0f ms (a rank stopped stepping?)",
+                    s->rank, s->wait_timeout_ms);
+    if (e & SLAB_ERR_FAR) return fail(CF_ERR_STATE, "rank %d: a particle moved further than the neighbouring slab in one step", s->rank);
+    if (e & SLAB_ERR_HALO)
+        return fail(CF_ERR_CAPACITY, "rank %d: a boundary layer exceeded the halo capacity (%d): raise halo_capacity", s->rank,
+                    s->mail.cap_halo);
+    if (e & SLAB_ERR_MIG)
+        return fail(CF_ERR_CAPACITY, "rank %d: leavers exceeded the migrant capacity (%d): raise migrant_capacity", s->rank,
+                    s->mail.cap_mig);
+    return fail(CF_ERR_CAPACITY, "rank %d would own more particles than its capacity %d", s->rank, s->cap_own);
+}
+
+static int slab_set_owned_count(cf_sim* s, int n) {
+    s->n = n;
+    s->h_slab[SLAB_NCUR] = n;
+    CU(cudaMemcpyAsync(s->d_slab + SLAB_NCUR, &s->h_slab[SLAB_NCUR], sizeof(int), cudaMemcpyHostToDevice, s->stream));
+    return 0;
+}
+
+extern "C" int cf_comm_init(cf_sim* s, int rank, int world, int capacity) {
     ARG(s && world >= 1 && rank >= 0 && rank < world && capacity >= 1);
     if (int rc = set_device(s)) return rc;
     CU(cudaStreamSynchronize(s->stream));
     slab_free(s);
-    if (world > 1) {
-        ARG(id128 != nullptr);
-        NcclApi& api = nccl_api();
-        if (!api.ok) return fail(CF_ERR_NCCL, "NCCL unavailable: %s", api.why);
-        ncclUniqueId id;
-        memcpy(&id, id128, 128);
-        NCCLCHK(api.CommInitRank(&s->comm, world, id, rank));
-    }
     s->rank = rank;
     s->world = world;
     s->slab = true;
     s->cap_own = capacity;
-    if (s->cap_halo <= 0) s->cap_halo = std::max(32768, capacity / 6);
-    if (s->cap_mig <= 0) s->cap_mig = std::max(16384, capacity / 20);
+    if (s->cap_halo <= 0) s->cap_halo = std::max(32768, capacity / 4);
+    if (s->cap_mig <= 0) s->cap_mig = std::max(16384, capacity / 16);
+    s->mail.cap_halo = s->cap_halo;
+    s->mail.cap_mig = s->cap_mig;
     s->n = 0;
+    s->bounds.clear();
     if (int rc = alloc_particle_buffers(s, s->cap_own + 2 * s->cap_halo)) return rc;
     s->base = s->cap_halo;
-    for (int d = 0; d < 2; d++) {
-        CU(cudaMalloc(&s->send_mig[d], slab_mig_bytes(s->cap_mig)));
-        CU(cudaMalloc(&s->recv_mig[d], slab_mig_bytes(s->cap_mig)));
-        CU(cudaMalloc(&s->send_halo[d], slab_halo_bytes(s->cap_halo)));
-        CU(cudaMalloc(&s->recv_halo[d], slab_halo_bytes(s->cap_halo)));
-        CU(cudaMalloc(&s->akeys[d], sizeof(uint32_t) * 2 * (size_t)s->cap_mig));
-        CU(cudaMalloc(&s->avals[d], sizeof(uint32_t) * 2 * (size_t)s->cap_mig));
-        CU(cudaMalloc(&s->gkeys[d], sizeof(uint32_t) * (size_t)s->cap_halo));
-        CU(cudaMemsetAsync(s->recv_mig[d], 0, slab_mig_bytes(s->cap_mig), s->stream));
-        CU(cudaMemsetAsync(s->recv_halo[d], 0, slab_halo_bytes(s->cap_halo), s->stream));
-    }
-    CU(cudaMalloc(&s->d_slab_counts, 8 * sizeof(int)));
-    CU(cudaMemsetAsync(s->d_slab_counts, 0, 8 * sizeof(int), s->stream));
-    CU(cudaMallocHost(&s->h_slab_counts, 8 * sizeof(int)));
+    for (int d = 0; d < 2; d++) CU(cudaMalloc(&s->gkeys[d], sizeof(uint32_t) * (size_t)s->cap_halo));
+    CU(cudaMalloc(&s->mailbox, s->mail.bytes()));
+    CU(cudaMemsetAsync(s->mailbox, 0, s->mail.bytes(), s->stream));
+    CU(cudaMalloc(&s->d_slab, SLAB_WORDS * sizeof(int)));
+    CU(cudaMemsetAsync(s->d_slab, 0, SLAB_WORDS * sizeof(int), s->stream));
+    CU(cudaMallocHost(&s->h_slab, SLAB_WORDS * sizeof(int)));
+    memset(s->h_slab, 0, SLAB_WORDS * sizeof(int));
+    s->seq_mig = s->seq_halo = 0;
+    s->mig_sent = false;
     CU(cudaStreamSynchronize(s->stream));
+    if (world == 1) { // loop-back: my own mailbox is both neighbours'
+        s->peer_box[0] = s->peer_box[1] = s->mailbox;
+        s->connected = true;
+    }
     return CF_OK;
 }
 
-// Ring exchange of two fixed-size messages.  What I send right arrives at my right neighbour
-// "from left", and vice versa.  Receives are posted right-then-left so that with world == 2
-// (both neighbours are the same peer) the peer's in-order sends (left, right) match.
-static int slab_exchange(cf_sim* s, char* send_left, char* send_right, char* recv_from_left,
-                         char* recv_from_right, size_t bytes) {
-    if (s->world == 1) {
-        CU(cudaMemcpyAsync(recv_from_left, send_right, bytes, cudaMemcpyDeviceToDevice, s->stream));
-        CU(cudaMemcpyAsync(recv_from_right, send_left, bytes, cudaMemcpyDeviceToDevice, s->stream));
-        return 0;
+extern "C" int cf_comm_mailbox_handle(cf_sim* s, void* handle64) {
+    ARG(s && handle64 && s->slab && s->mailbox);
+    if (int rc = set_device(s)) return rc;
+    static_assert(sizeof(cudaIpcMemHandle_t) == CF_IPC_HANDLE_BYTES, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, s->mailbox));
+    memcpy(handle64, &h, sizeof(h));
+    return CF_OK;
+}
+
+extern "C" int cf_comm_connect(cf_sim* s, const void* left_handle64, const void* right_handle64) {
+    ARG(s && s->slab && s->mailbox);
+    if (int rc = set_device(s)) return rc;
+    if (s->world == 1) return CF_OK;
+    ARG(left_handle64 && right_handle64);
+    const void* hs[2] = {left_handle64, right_handle64};
+    for (int d = 0; d < 2; d++) {
+        if (d == 1 && s->world == 2) { // both neighbours are the same rank: one mapping
+            s->peer_box[1] = s->peer_box[0];
+            break;
+        }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, hs[d], sizeof(h));
+        void* p = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess)
+            return fail(CF_ERR_CUDA, "cudaIpcOpenMemHandle (%s neighbour) failed: %s — the ranks of a slab run need peer access "
+                        "(NVLink / NVSwitch or PCIe P2P) between their GPUs", d ? "right" : "left", cudaGetErrorString(e));
+        s->peer_box[d] = (char*)p;
     }
-    NcclApi& api = nccl_api();
-    int left = (s->rank - 1 + s->world) % s->world, right = (s->rank + 1) % s->world;
-    NCCLCHK(api.GroupStart());
-    NCCLCHK(api.Send(send_left, bytes, ncclChar_, left, s->comm, s->stream));
-    NCCLCHK(api.Send(send_right, bytes, ncclChar_, right, s->comm, s->stream));
-    NCCLCHK(api.Recv(recv_from_right, bytes, ncclChar_, right, s->comm, s->stream));
-    NCCLCHK(api.Recv(recv_from_left, bytes, ncclChar_, left, s->comm, s->stream));
-    NCCLCHK(api.GroupEnd());
-    return 0;
+    s->connected = true;
+    return CF_OK;
 }
 
-// Elements actually shipped per message.  Buffers are allocated for cap_halo / cap_mig, but a
-// fixed-size message of that capacity would move ~30 MB per step and rank; both ends of a link
-// instead derive the same tighter bound from numbers every rank knows (global count, world size,
-// owned layers): 2x the mean ghost layer + 8192, mean/64 + 16384 migrants.  A rank that would
-// exceed it fails with CF_ERR_CAPACITY (raise it with the halo_slack / migrant_slack options).
-static int slab_halo_msg_cap(const cf_sim* s) {
-    if (s->n_total <= 0) return s->cap_halo; // global count unknown: full (identical) capacity
-    double mean = (double)s->n_total / s->world / std::max(s->nxl, 1);
-    long long cap = (long long)(s->halo_slack * mean) + 8192;
-    return (int)std::min<long long>(cap, s->cap_halo);
-}
-static int slab_mig_msg_cap(const cf_sim* s) {
-    if (s->n_total <= 0) return s->cap_mig;
-    double mean = (double)s->n_total / s->world;
-    long long cap = (long long)(s->mig_slack * mean / 64.0) + 16384;
-    return (int)std::min<long long>(cap, s->cap_mig);
+extern "C" int cf_slab_set_bounds(cf_sim* s, const float* bounds, int count) {
+    ARG(s && s->slab && bounds && count == s->world + 1);
+    for (int r = 0; r < s->world; r++) ARG(bounds[r + 1] > bounds[r]);
+    ARG(bounds[0] == 0.0f);
+    if (s->mig_sent) return fail(CF_ERR_STATE, "cf_slab_set_bounds: a migrant exchange is pending (build the cell list or sync first)");
+    s->bounds.assign(bounds, bounds + count);
+    s->sorted_valid = false;
+    return CF_OK;
 }
 
-static int slab_check_flags(cf_sim* s) {
-    int f = s->h_slab_counts[3];
-    if (f == 1) return fail(CF_ERR_STATE, "a particle moved further than one slab width in one step");
-    if (f == 2)
-        return fail(CF_ERR_CAPACITY, "a ghost layer exceeded the halo message capacity (%d): raise halo_slack",
-                    slab_halo_msg_cap(s));
-    return 0;
-}
-
-// Host-side wall-clock breakdown of the slab cell-list build (CF_SLAB_DEBUG=1 prints it at
-// cf_destroy): where a rank waits — its own GPU (sync after the sort) or its neighbours.
-struct SlabHostTimes {
-    double sort_sync = 0, mig_sync = 0, enqueue = 0;
-    double gpu_mig = 0, gpu_mid = 0, gpu_halo = 0; // device time: migrant exchange, merge/reorder, halo exchange
-    long long calls = 0;
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-};
-static thread_local SlabHostTimes g_slab_times;
-static double wall_now() {
-    timespec ts;
-    clock_gettime(CLOCK_MONOTONIC, &ts);
-    return ts.tv_sec + 1e-9 * ts.tv_nsec;
-}
-
-// Cell-list build in slab mode: classify + sort, migrate, merge, reorder, bounds, ghost exchange.
-static int ensure_sorted_slab(cf_sim* s, cudaEvent_t ev_x0, cudaEvent_t ev_x1) {
+// Cell-list build in slab mode, all on the device: (emit migrants,) wait + append arrivals, one class sort,
+// reorder + bounds (new owned count), halo pack -> neighbours' mailboxes, wait + unpack ghosts, ghost bounds.
+static int ensure_sorted_slab(cf_sim* s, cudaEvent_t* ev_x) {
     if (s->sorted_valid) return 0;
-    const double t_begin = wall_now();
+    if (!s->connected) return fail(CF_ERR_STATE, "slab mode: cf_comm_connect has not been called");
     const int cur = s->cur, nxt = cur ^ 1;
     const int B = s->base;
-    int n = s->n;
+    const int NU = s->cap_own; // launch bound of everything that walks the owned particles
     const long long KC = (long long)s->ncell * CF_KEY_SUB;
     s->geom.class_stride = (uint32_t)KC;
+    const SlabPeers P = slab_peers(s);
+    const unsigned long long tmo = (unsigned long long)(s->wait_timeout_ms * 1e6);
+    // ---- migrants: emitted by the previous step's integrate kernel, or here after an upload / spawn / move ----
+    if (!s->mig_sent) {
+        s->seq_mig++;
+        LAUNCH(s, slab_emit_migrants_kernel, div_up(NU, 256), 256, 0, s->pos[cur] + B, s->vel[cur] + B, s->id[cur] + B, NU,
+               s->geom, P, s->seq_mig);
+    }
+    s->mig_sent = false;
+    if (ev_x) CU(cudaEventRecord(ev_x[0], s->stream));
+    const int mpar = s->seq_mig & 1;
+    LAUNCH(s, slab_wait_kernel, 1, 32, 0, s->mail.flag_mig(s->mailbox, 0), s->mail.flag_mig(s->mailbox, 1), s->seq_mig,
+           s->d_slab, tmo);
+    LAUNCH(s, slab_unpack_arrivals_kernel, 1, 1024, 0, s->mailbox, s->mail, mpar, s->pos[cur] + B, s->vel[cur] + B,
+           s->id[cur] + B, s->cap_own, s->d_slab);
+    if (ev_x) CU(cudaEventRecord(ev_x[1], s->stream));
+    // ---- one sort: stayers + arrivals by cell, leavers behind them ----
     int src = 0;
-    int n_stay = 0, n_left = 0, n_right = 0;
-    if (n > 0) {
-        LAUNCH(s, slab_key_kernel, div_up(n, 256), 256, 0, s->pos[cur] + B, s->keys[0], s->vals[0], n, s->sc, s->geom,
-               s->d_slab_counts + 3);
-        if (int rc = radix_sort_pairs(s, s->keys, s->vals, n, 3 * KC, &src)) return rc;
-        LAUNCH(s, slab_class_counts_kernel, 1, 32, 0, s->keys[src], n, (uint32_t)KC, s->d_slab_counts);
-    } else {
-        CU(cudaMemsetAsync(s->d_slab_counts, 0, 3 * sizeof(int), s->stream));
-    }
-    const int mcap = slab_mig_msg_cap(s), hcap = slab_halo_msg_cap(s);
-    if (ev_x0) CU(cudaEventRecord(ev_x0, s->stream));
-    const bool dbg = getenv("CF_SLAB_DEBUG") != nullptr;
-    if (dbg && !g_slab_times.ev[0])
-        for (int i = 0; i < 4; i++) cudaEventCreate(&g_slab_times.ev[i]);
-    if (dbg) cudaEventRecord(g_slab_times.ev[0], s->stream);
-    // ---- migrants: packed with device-side counts, so nothing waits for the host here ----
-    LAUNCH(s, slab_pack_migrants_kernel, div_up(2 * mcap, 256), 256, 0, s->vals[src], s->pos[cur] + B, s->vel[cur] + B,
-           s->id[cur] + B, s->d_slab_counts, s->send_mig[0], s->send_mig[1], mcap);
-    if (int rc = slab_exchange(s, s->send_mig[0], s->send_mig[1], s->recv_mig[0], s->recv_mig[1],
-                               slab_mig_bytes(mcap)))
+    if (int rc = radix_sort_run<SlabKeyFn, true>(s, SlabKeyFn{s->pos[cur] + B, s->sc, s->geom, s->d_slab}, s->keys, s->vals, NU,
+                                                 s->d_slab + SLAB_NTMP, 2 * KC, &src))
         return rc;
-    // the only host synchronisation of the cell-list build: class counts + arrival counts
-    CU(cudaMemcpyAsync(s->h_slab_counts, s->d_slab_counts, 4 * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
-    CU(cudaMemcpyAsync(&s->h_slab_counts[6], mig_count(s->recv_mig[0], mcap), sizeof(int),
-                       cudaMemcpyDeviceToHost, s->stream));
-    CU(cudaMemcpyAsync(&s->h_slab_counts[7], mig_count(s->recv_mig[1], mcap), sizeof(int),
-                       cudaMemcpyDeviceToHost, s->stream));
-    if (dbg) cudaEventRecord(g_slab_times.ev[1], s->stream);
-    const double t_s1 = wall_now();
-    CU(cudaStreamSynchronize(s->stream));
-    if (g_slab_times.calls >= 5) g_slab_times.mig_sync += wall_now() - t_s1;
-    if (int rc = slab_check_flags(s)) return rc;
-    n_stay = s->h_slab_counts[0], n_left = s->h_slab_counts[1], n_right = s->h_slab_counts[2];
-    if (n_left > mcap || n_right > mcap)
-        return fail(CF_ERR_CAPACITY, "%d/%d migrants exceed the migrant message capacity (%d): raise migrant_slack",
-                    n_left, n_right, mcap);
-    const int n_al = s->h_slab_counts[6], n_ar = s->h_slab_counts[7], n_a = n_al + n_ar;
-    const int n_new = n_stay + n_a;
-    if (n + n_a > s->cap_own || n_new > s->cap_own)
-        return fail(CF_ERR_CAPACITY, "rank %d would own %d particles, capacity %d", s->rank, n_new, s->cap_own);
-
-    uint32_t* fkeys = s->keys[src];
-    uint32_t* fvals = s->vals[src];
-    if (n_a > 0) {
-        LAUNCH(s, slab_unpack_arrivals_kernel, div_up(n_a, 256), 256, 0, s->recv_mig[0], s->recv_mig[1], n_al, n_ar,
-               mcap, s->pos[cur] + B, s->vel[cur] + B, s->id[cur] + B, n, s->akeys[0], s->avals[0], s->sc);
-        int asrc = 0;
-        if (int rc = radix_sort_pairs(s, s->akeys, s->avals, n_a, KC, &asrc)) return rc;
-        LAUNCH(s, slab_merge_kernel, div_up(n_new, 256), 256, 0, s->keys[src], s->vals[src], n_stay, s->akeys[asrc],
-               s->avals[asrc], n_a, s->keys[src ^ 1], s->vals[src ^ 1]);
-        fkeys = s->keys[src ^ 1];
-        fvals = s->vals[src ^ 1];
-        src ^= 1;
-    }
-    // ---- reorder into the other buffer, cell bounds of the owned layers ----
-    LAUNCH(s, reorder_bounds_kernel, div_up(std::max(n_new, s->ncell + 1), 256), 256, 0, fvals, fkeys, s->pos[cur] + B,
-           s->vel[cur] + B, s->id[cur] + B, s->pos[nxt] + B, s->vel[nxt] + B, s->id[nxt] + B, n_new, nullptr,
-           s->cell_start, s->ncell, B, nullptr);
+    LAUNCH(s, reorder_bounds_kernel, div_up(std::max(NU, s->ncell + 1), 256), 256, 0, s->vals[src], s->keys[src],
+           s->pos[cur] + B, s->vel[cur] + B, s->id[cur] + B, s->pos[nxt] + B, s->vel[nxt] + B, s->id[nxt] + B, NU,
+           s->d_slab + SLAB_NTMP, s->cell_start, s->ncell, B, s->d_slab + SLAB_NCUR);
     if (src != 0) std::swap(s->keys[0], s->keys[1]), std::swap(s->vals[0], s->vals[1]);
     s->cur = nxt;
-    s->n = n_new;
-
     // ---- ghost layers ----
-    if (dbg) cudaEventRecord(g_slab_times.ev[2], s->stream);
+    if (ev_x) CU(cudaEventRecord(ev_x[2], s->stream));
     const int layer_cells = s->sc.dims[1] * s->sc.dims[2];
-    LAUNCH(s, slab_pack_halo_kernel, div_up(hcap, 256), 256, 0, s->pos[nxt], s->id[nxt], s->cell_start,
-           layer_cells, s->nxl, s->send_halo[0], s->send_halo[1], hcap, s->d_slab_counts + 3);
-    if (int rc = slab_exchange(s, s->send_halo[0], s->send_halo[1], s->recv_halo[0], s->recv_halo[1],
-                               slab_halo_bytes(hcap)))
-        return rc;
-    LAUNCH(s, slab_unpack_ghosts_kernel, div_up(hcap, 256), 256, 0, s->recv_halo[0], s->recv_halo[1], hcap,
-           s->pos[nxt], s->id[nxt], B, n_new, s->gkeys[0], s->gkeys[1], s->sc);
-    LAUNCH(s, slab_ghost_bounds_kernel, div_up(2 * layer_cells + 1, 256), 256, 0, s->gkeys[0], s->gkeys[1],
-           s->recv_halo[0], s->recv_halo[1], hcap, s->cell_start, layer_cells, s->ncell, B, n_new, s->d_slab_counts + 4);
-    if (ev_x1) CU(cudaEventRecord(ev_x1, s->stream));
+    s->seq_halo++;
+    const int hpar = s->seq_halo & 1;
+    LAUNCH(s, slab_pack_halo_kernel, div_up(s->cap_halo, 256), 256, 0, s->pos[nxt], s->id[nxt], s->cell_start, layer_cells,
+           s->nxl, P, s->seq_halo);
+    LAUNCH(s, slab_wait_kernel, 1, 32, 0, s->mail.flag_halo(s->mailbox, 0), s->mail.flag_halo(s->mailbox, 1), s->seq_halo,
+           s->d_slab, tmo);
+    LAUNCH(s, slab_unpack_ghosts_kernel, div_up(s->cap_halo, 256), 256, 0, s->mailbox, s->mail, hpar, s->pos[nxt], s->id[nxt],
+           B, s->d_slab, s->gkeys[0], s->gkeys[1], s->sc);
+    LAUNCH(s, slab_ghost_bounds_kernel, div_up(2 * layer_cells + 1, 256), 256, 0, s->gkeys[0], s->gkeys[1], s->mailbox, s->mail,
+           hpar, s->cell_start, layer_cells, s->ncell, B, s->d_slab);
+    if (ev_x) CU(cudaEventRecord(ev_x[3], s->stream));
     s->sorted_valid = true;
     CU(cudaGetLastError());
-    if (dbg) {
-        cudaEventRecord(g_slab_times.ev[3], s->stream);
-        cudaEventSynchronize(g_slab_times.ev[3]);
-        float a = 0, b = 0, c = 0;
-        cudaEventElapsedTime(&a, g_slab_times.ev[0], g_slab_times.ev[1]);
-        cudaEventElapsedTime(&b, g_slab_times.ev[1], g_slab_times.ev[2]);
-        cudaEventElapsedTime(&c, g_slab_times.ev[2], g_slab_times.ev[3]);
-        if (g_slab_times.calls >= 5) g_slab_times.gpu_mig += a, g_slab_times.gpu_mid += b, g_slab_times.gpu_halo += c;
-    }
-    if (g_slab_times.calls >= 5) g_slab_times.enqueue += wall_now() - t_begin;
-    g_slab_times.calls++;
     return 0;
+}
+
+// A pending migrant exchange (sent by the last step's integrate) must be consumed before the state is
+// replaced or shifted: every rank does this collectively, like the build itself.
+static int prepare_step_const(cf_sim* s);
+static int slab_drain(cf_sim* s) {
+    if (!s->slab || !s->mig_sent) return 0;
+    if (int rc = prepare_step_const(s)) return rc;
+    return ensure_sorted_slab(s, nullptr);
 }
 
 // Global initial condition in slab mode: every rank generates all n_total particles (counter-
@@ -253,12 +227,10 @@ static int ensure_sorted_slab(cf_sim* s, cudaEvent_t ev_x0, cudaEvent_t ev_x1) {
 // lies in its slab.
 static int slab_init_particles(cf_sim* s, long long n_total, uint64_t seed, int mode) {
     ARG(n_total >= 0 && n_total < (1ll << 31));
+    if (int rc = slab_drain(s)) return rc;
     const int N = (int)n_total;
     s->n_total = n_total;
-    s->geom.x_lo = slab_bound(s, s->rank);
-    s->geom.x_hi = slab_bound(s, s->rank + 1);
-    s->geom.W = s->params.canvasWidth;
-    s->geom.slab_w = s->params.canvasWidth / (float)s->world;
+    slab_update_geom(s);
     float4 *tp = nullptr, *tv = nullptr, *tf = nullptr;
     int* ti = nullptr;
     uint32_t *k[2] = {nullptr, nullptr}, *v[2] = {nullptr, nullptr};
@@ -282,14 +254,14 @@ static int slab_init_particles(cf_sim* s, long long n_total, uint64_t seed, int 
         int src = 0;
         rc = radix_sort_pairs(s, k, v, N, 2, &src);
         if (rc == 0) {
-            LAUNCH(s, slab_class_counts_kernel, 1, 32, 0, k[src], N, 1u, s->d_slab_counts);
-            if (cudaMemcpyAsync(s->h_slab_counts, s->d_slab_counts, 3 * sizeof(int), cudaMemcpyDeviceToHost,
+            LAUNCH(s, slab_count_mine_kernel, 1, 32, 0, k[src], N, s->d_slab + SLAB_NTMP);
+            if (cudaMemcpyAsync(&s->h_slab[SLAB_NTMP], s->d_slab + SLAB_NTMP, sizeof(int), cudaMemcpyDeviceToHost,
                                 s->stream) != cudaSuccess ||
                 cudaStreamSynchronize(s->stream) != cudaSuccess)
                 rc = fail(CF_ERR_CUDA, "slab init sync failed");
         }
         if (rc == 0) {
-            mine = s->h_slab_counts[0];
+            mine = s->h_slab[SLAB_NTMP];
             if (mine > s->cap_own) rc = fail(CF_ERR_CAPACITY, "rank %d owns %d particles, capacity %d", s->rank, mine, s->cap_own);
         }
         if (rc == 0 && mine > 0)
@@ -300,7 +272,7 @@ static int slab_init_particles(cf_sim* s, long long n_total, uint64_t seed, int 
     cudaFree(tp), cudaFree(tv), cudaFree(tf), cudaFree(ti);
     for (int b = 0; b < 2; b++) cudaFree(k[b]), cudaFree(v[b]);
     if (rc) return rc;
-    s->n = mine;
+    if (int rc2 = slab_set_owned_count(s, mine)) return rc2;
     s->sorted_valid = false;
     return CF_OK;
 }

@@ -1,9 +1,10 @@
 """One-process-per-GPU glue for the slab-decomposed engine.
 
 torch.distributed is used for plumbing only: rendezvous (RANK / WORLD_SIZE / MASTER_* from the
-environment, as torch.distributed.run sets them), broadcasting the NCCL unique id the C library
-creates, gathering results and reducing timings.  The per-step halo / migration exchange is done
-inside the C library with ncclSend/ncclRecv on the engine's stream (csrc/slab_host.inl).
+environment, as torch.distributed.run sets them), exchanging the CUDA IPC handles of the ranks'
+mailboxes once at start-up, gathering results and reducing timings.  The per-step halo / migration
+exchange is done inside the C library's own kernels, which store straight into the neighbours'
+mailboxes over NVLink (csrc/kernels_slab.cuh, csrc/slab_host.inl): no collective call per step.
 
 Everything here that does not touch a GPU (slab bounds, partition / gather of particle arrays,
 max-over-ranks reductions, id broadcast) also runs on the `gloo` backend; tests/test_dist_cpu.py
@@ -80,16 +81,24 @@ def broadcast_bytes(data: bytes | None, nbytes: int, src: int = 0) -> bytes:
     return bytes(t.cpu().numpy().tobytes())
 
 
-def nccl_unique_id() -> bytes:
-    """Rank 0 asks the C library for an ncclUniqueId; everybody gets it."""
+def all_gather_bytes(data: bytes) -> list:
+    """Every rank's byte string, in rank order (works on gloo and nccl)."""
     import torch.distributed as dist
 
-    ident = None
-    if not dist.is_initialized() or dist.get_rank() == 0:
-        buf = C.create_string_buffer(128)
-        _lib.check(_lib.lib().cf_nccl_unique_id(buf))
-        ident = buf.raw
-    return broadcast_bytes(ident, 128, 0)
+    if not dist.is_initialized():
+        return [data]
+    out = [None] * dist.get_world_size()
+    dist.all_gather_object(out, data)
+    return out
+
+
+def connect_ring(sim, rank: int, world: int):
+    """Exchange the mailbox handles and map the two ring neighbours' mailboxes into this rank."""
+    if world == 1:
+        return
+    handles = all_gather_bytes(sim.mailboxHandle())
+    sim.connect(handles[(rank - 1) % world], handles[(rank + 1) % world])
+    barrier()  # every rank has mapped its neighbours before anybody starts stepping
 
 
 def all_reduce_max(value: float) -> float:
@@ -168,10 +177,10 @@ def make_slab_sim(params, raw, radio, n_total, seed, mode, capacity_factor=1.5, 
     else:
         sim.setRawForceTableValues(raw)
         sim.updateForceTable(params.forceRange, params.forceBias, params.forceOffset)
-    ident = nccl_unique_id() if world > 1 else None
     capacity = int(n_total / world * capacity_factor) + 1024
-    sim.commInit(rank, world, ident, capacity)
-    sim.setOption("global_particle_count", n_total)   # lets both ends of a link agree on tight message sizes
+    sim.setOption("global_particle_count", n_total)   # the cell grid derives from rank-invariant numbers only
+    sim.commInit(rank, world, capacity)
+    connect_ring(sim, rank, world)
     if seed is not None:
         sim.initParticlesGlobal(n_total, seed, mode)
     return sim, rank, world
@@ -273,7 +282,7 @@ def bench_multi(args, workloads, workload_setup):
                        "mean_neighbours": round(accepted / max(owned, 1), 1),
                        "graph": list(graph) if graph else None,
                        "l2": "flushed between timed steps (256 MiB overwrite)",
-                       "parallelism": f"{world} x-slabs, NCCL halo+migration exchange per step",
+                       "parallelism": f"{world} x-slabs, peer-to-peer mailbox halo+migration exchange per step (NVLink stores, no collective)",
                        "timing": "CUDA events per rank, max over ranks"},
             "e2e": {"value": round(n_total / e2e_s, 1), "unit": METRIC, "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": round(e2e_s * 1e3, 4),

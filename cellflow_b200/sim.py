@@ -224,12 +224,28 @@ class ParticleSimulation:
         return xyzt, counts
 
     # -- multi-GPU slabs (one process per GPU) ----------------------------------------------------
-    def commInit(self, rank: int, world: int, nccl_id: bytes | None, capacity: int):
-        """Rank `rank` of `world` owns x in [rank*W/world, (rank+1)*W/world).  world == 1 runs the
-        same slab code path with device-local copies instead of NCCL."""
-        buf = C.create_string_buffer(nccl_id, 128) if nccl_id is not None else None
+    def commInit(self, rank: int, world: int, capacity: int):
+        """Rank `rank` of `world` owns one x slab (uniform split unless setSlabBounds says otherwise).
+        world == 1 runs the same slab code path with the rank's own mailbox as both neighbours; world > 1
+        needs mailboxHandle() of both ring neighbours passed to connect() (cellflow_b200/dist.py does it)."""
         check(self._L.cf_set_params(self._h, C.byref(self.params)))
-        check(self._L.cf_comm_init(self._h, C.c_int(rank), C.c_int(world), buf, C.c_int(capacity)))
+        check(self._L.cf_comm_init(self._h, C.c_int(rank), C.c_int(world), C.c_int(capacity)))
+        self._slab_capacity = capacity
+
+    def mailboxHandle(self) -> bytes:
+        """CUDA IPC handle (64 bytes) of this rank's mailbox, for the two ring neighbours."""
+        buf = C.create_string_buffer(64)
+        check(self._L.cf_comm_mailbox_handle(self._h, buf))
+        return buf.raw
+
+    def connect(self, left_handle: bytes, right_handle: bytes):
+        check(self._L.cf_comm_connect(self._h, C.create_string_buffer(left_handle, 64),
+                                      C.create_string_buffer(right_handle, 64)))
+
+    def setSlabBounds(self, bounds):
+        b = np.ascontiguousarray(bounds, dtype=np.float32)
+        check(self._L.cf_set_params(self._h, C.byref(self.params)))
+        check(self._L.cf_slab_set_bounds(self._h, _p(b), C.c_int(len(b))))
 
     def initParticlesGlobal(self, n_total: int, seed: int, mode=_lib.INIT_UNIFORM):
         check(self._L.cf_set_params(self._h, C.byref(self.params)))
@@ -250,7 +266,7 @@ class ParticleSimulation:
 
     def downloadOwned(self):
         """(particles, counts, ids) of the particles this rank currently owns (slot order)."""
-        cap = max(self.getParticleCount(), 1)
+        cap = max(getattr(self, "_slab_capacity", 0), self.getParticleCount(), 1)
         out = np.zeros(cap, dtype=PARTICLE)
         counts = np.zeros(cap, dtype=np.int32)
         ids = np.zeros(cap, dtype=np.int32)

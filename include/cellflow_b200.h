@@ -38,7 +38,7 @@ typedef enum cf_status {
     CF_ERR_CUDA = -2,     /* CUDA runtime error (message in cf_last_error) */
     CF_ERR_STATE = -3,    /* call not valid in the handle's current state */
     CF_ERR_IO = -4,       /* preset file could not be read / parsed */
-    CF_ERR_NCCL = -5,     /* NCCL error or NCCL not loadable */
+    CF_ERR_NCCL = -5,     /* (reserved; round 1 used NCCL for the slab exchange) */
     CF_ERR_CAPACITY = -6  /* a fixed-capacity buffer (halo, migrants, edges) overflowed */
 } cf_status;
 
@@ -231,12 +231,23 @@ int cf_apply_preset(cf_sim* sim, const cf_preset* preset);
 
 /* ---- multi-GPU slabs (new; no reference counterpart) ---------------- */
 
-int cf_nccl_unique_id(void* id128);  /* 128 bytes; rank 0 creates, host broadcasts */
-/* Rank `rank` of `world` owns x in [rank*W/world, (rank+1)*W/world).  `capacity` bounds the
- * owned particle count of this rank and must be the same on every rank (message sizes derive
- * from it, or from the option "global_particle_count" when that is set, identically, on all
- * ranks). */
-int cf_comm_init(cf_sim* sim, int rank, int world, const void* id128, int capacity);
+/* Rank `rank` of `world` owns x in [bound(rank), bound(rank+1)) — the uniform split rank*W/world unless
+ * cf_slab_set_bounds says otherwise.  `capacity` bounds the owned particle count of this rank and must be the
+ * same on every rank (the cell grid and the mailbox sizes derive from rank-invariant numbers only: the
+ * capacity, and the options "global_particle_count", "halo_capacity", "migrant_capacity").
+ * Neighbour exchange is peer-to-peer: every rank owns a mailbox in device memory that its two ring neighbours
+ * map through CUDA IPC and write with plain stores over NVLink from inside the producing kernels.  Setup:
+ *   cf_comm_init on every rank -> cf_comm_mailbox_handle -> the host exchanges the 64-byte handles (any transport)
+ *   -> cf_comm_connect(left neighbour's handle, right neighbour's handle).
+ * world == 1 needs no connect (the rank's own mailbox stands in for both neighbours). */
+#define CF_IPC_HANDLE_BYTES 64
+int cf_comm_init(cf_sim* sim, int rank, int world, int capacity);
+int cf_comm_mailbox_handle(cf_sim* sim, void* handle64);
+int cf_comm_connect(cf_sim* sim, const void* left_handle64, const void* right_handle64);
+/* Slab bounds for clustered states: world + 1 increasing x values, bounds[0] = 0, bounds[world] = canvas width,
+ * the same array on every rank; every slab must stay at least one interaction radius wide.  Call it between
+ * steps, after the particles have been redistributed to match (cellflow_b200/dist.py: rebalance). */
+int cf_slab_set_bounds(cf_sim* sim, const float* bounds, int count);
 /* Slab-mode initial condition: every rank generates the same n_total particles (counter-based
  * generator) and keeps those whose x lies in its slab.  Canvas = params last set. */
 int cf_init_particles_global(cf_sim* sim, int64_t n_total, uint64_t seed, int mode);
@@ -252,7 +263,7 @@ int cf_download_particles_ids(cf_sim* sim, cf_particle* aos, int32_t* counts, in
 
 int cf_get_stats(cf_sim* sim, cf_stats* stats);
 int cf_stats_reset(cf_sim* sim);
-/* Sorted-order views for the cell-assignment parity tests: sort key (= cell * 64 + Morton code of the 4x4x4 sub-cell) and
+/* Sorted-order views for the cell-assignment parity tests: sort key (= cell * 64 + Hilbert index of the 4x4x4 sub-cell) and
  * original id per slot. */
 int cf_download_cell_keys(cf_sim* sim, uint32_t* keys, int32_t* ids, int capacity, int* count);
 /* Tuning knobs; every one defaults to the automatic choice and none changes a result beyond the
@@ -263,8 +274,9 @@ int cf_download_cell_keys(cf_sim* sim, uint32_t* keys, int32_t* ids, int capacit
  *   "cuda_graphs"    1 (default): single-GPU step and graph build replay captured CUDA graphs
  *   "timing"         0 off | 1 events between the phases of a step | 2 events around whole steps
  *   "max_cells_per_particle"   upper bound of grid cells per particle (default 16)
- *   "global_particle_count", "halo_slack", "migrant_slack", "halo_capacity", "migrant_capacity"
- *                    slab-mode message sizing (the two capacities before cf_comm_init)
+ *   "global_particle_count", "halo_capacity", "migrant_capacity"
+ *                    slab mode, the same on every rank: grid sizing / mailbox capacities (before cf_comm_init)
+ *   "wait_timeout_ms"  slab mode: how long a rank waits for a neighbour's message before it reports an error
  * Unknown names return CF_ERR_ARG. */
 int cf_set_option(cf_sim* sim, const char* name, double value);
 /* Measurement helpers for bench.py (not on the simulation path): live FP32 FMA peak of the

@@ -17,49 +17,78 @@ import oracle as O  # noqa: E402
 import util as U  # noqa: E402
 
 
-def main():
-    rank, world = cfd.init_process_group("nccl")
-    p, table, radio = U.config("pulser", delta_t=0.9)      # large dt: visible migration per step
-    n = 120_000
-    state, counts = U.random_state(n, 6, 23, p.canvas, "uniform", vel_scale=60.0)
+def run_case(name, p, table, radio, state, counts, steps, graph, rank, world):
+    import torch.distributed as dist
+    n = len(state)
     lp = U.to_lib_params(p)
     sim, rank, world = cfd.make_slab_sim(lp, None, radio, n, None, cf.INIT_UNIFORM, force_table=table)
     mine, mcounts, ids = cfd.partition(state, counts, p.canvasWidth, rank, world)
     sim.uploadOwned(mine, mcounts, ids)
     want_state, want_counts = state, counts
     first_ids = set(ids.tolist())
-    for step in range(4):
+    for step in range(steps):
         sim.simulate()
         pp, cc, ii = sim.downloadOwned()
         got, gcnt = cfd.gather_particles(pp, cc, ii, n)
-        edges, _ = sim.generateProximityGraph(200.0, 5)
-        import torch.distributed as dist
-        all_edges = [None] * world if rank == 0 else None
-        dist.gather_object(edges.tobytes(), all_edges, dst=0)
+        all_edges = None
+        if graph:
+            edges, _ = sim.generateProximityGraph(*graph)
+            all_edges = [None] * world if rank == 0 else None
+            dist.gather_object(edges.tobytes(), all_edges, dst=0)
+        else:
+            sim.cellKeys()  # consumes the pending migrant exchange like the graph build does
         if rank == 0:
             want, wcnt, fabs = O.step(want_state, want_counts, p, table, radio, "cells", 8)
-            assert np.array_equal(gcnt, wcnt), f"step {step}: counts differ on {(gcnt != wcnt).sum()} particles"
+            assert np.array_equal(gcnt, wcnt), f"{name} step {step}: counts differ on {(gcnt != wcnt).sum()} particles"
             mult = U.force_multiplier_of(p, wcnt, want_counts)
             rel = U.force_rel_err(got["acc"], want["acc"], fabs, mult).max()
-            assert rel <= U.FORCE_RTOL, rel
-            es = set()
-            for b in all_edges:
-                e = np.frombuffer(b, cf.EDGE)
-                es |= U.edge_set(e)
-            assert es == U.edge_set(O.graph(got, 200.0, 5, canvas=p.canvas, method="cells")), f"step {step}: edges"
+            assert rel <= U.FORCE_RTOL, (name, rel)
+            if graph:
+                es = set()
+                for b in all_edges:
+                    es |= U.edge_set(np.frombuffer(b, cf.EDGE))
+                assert es == U.edge_set(O.graph(got, graph[0], graph[1], canvas=p.canvas, method="cells")), f"{name} step {step}: edges"
             want_state, want_counts = got, gcnt
         # every rank continues from its own device state (no re-upload): real migration
-    # migration is applied by the cell-list build that follows a step (the graph build above)
+    # migration is applied by the cell-list build that follows a step (the graph build / cellKeys above)
     pp, _, ii = sim.downloadOwned()
     total_migrated = cfd.all_reduce_sum(float(len(set(ii.tolist()) - first_ids)))
     lo, hi = sim.slabBounds()
-    assert np.all((pp["pos"][:, 0] >= lo) & (pp["pos"][:, 0] < hi)), "a rank holds a particle outside its slab"
+    assert np.all((pp["pos"][:, 0] >= lo) & (pp["pos"][:, 0] < hi)), f"{name}: a rank holds a particle outside its slab"
     st = sim.stats()
+    # the cell grid must be the same on every rank (it once depended on the rank's own count)
+    grids = cfd.all_gather_bytes(bytes(np.int32(list(st.grid)[1:]).tobytes()))
+    assert len(set(grids)) == 1, f"{name}: ranks disagree on the (y, z) grid: {[np.frombuffer(g, np.int32).tolist() for g in grids]}"
     if rank == 0:
-        assert total_migrated > 0, "test did not exercise migration"
-        print(f"DIST_CHECK_OK world={world} migrated={int(total_migrated)} ghosts_rank0={st.n_ghost}", flush=True)
+        print(f"DIST_CASE_OK {name} world={world} n={n} steps={steps} migrated={int(total_migrated)} "
+              f"ghosts_rank0={st.n_ghost} grid={list(st.grid)} force_kernel={st.force_kernel}", flush=True)
     sim.close()
     cfd.barrier()
+    return int(total_migrated)
+
+
+def main():
+    rank, world = cfd.init_process_group("nccl")
+    # A. dense, uniform radius: large dt so that every step migrates particles; graph on
+    p, table, radio = U.config("pulser", delta_t=0.9)
+    state, counts = U.random_state(120_000, 6, 23, p.canvas, "uniform", vel_scale=60.0)
+    mig = run_case("pulser-120k", p, table, radio, state, counts, 4, (200.0, 5), rank, world)
+    # B. per-type radii (type-sorted j copy over owned + ghost slots), clustered cube, graph on
+    p, table, _ = U.config("eater", ratioWithLFO=0.5, delta_t=0.5)
+    radio = np.float32([1.0, 0.5, 0.0, 0.0, -0.5, 1.0])
+    state, counts = U.random_state(90_000, 6, 29, p.canvas, "uniform", vel_scale=80.0)
+    run_case("eater-radii-90k", p, table, radio, state, counts, 3, (200.0, 5), rank, world)
+    # C. small radius, low density: the grid is bound by cells-per-particle, not by the radius — the regime
+    #    in which a grid derived from the rank's own count differs between ranks (default preset, 100 k)
+    p = O.Params()
+    raw, radio = O.default_tables(6)
+    table = O.force_table(raw, 6, p.forceRange, p.forceBias, p.forceOffset)
+    state, counts = U.random_state(100_000, 6, 31, p.canvas, "uniform", vel_scale=300.0)
+    #    (no graph here: the rule's 200 exceeds the one-cell ghost layer of this fine grid, which slab mode refuses)
+    run_case("default-100k-sparse", p, table, radio, state, counts, 3, None, rank, world)
+    if rank == 0:
+        assert mig > 0, "test did not exercise migration"
+        print(f"DIST_CHECK_OK world={world} migrated={mig}", flush=True)
 
 
 if __name__ == "__main__":

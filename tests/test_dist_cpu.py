@@ -1,5 +1,5 @@
 """CPU tests of the one-process-per-GPU host logic (cellflow_b200/dist.py) on the gloo backend,
-world_size 2: rendezvous from the environment, byte broadcast (the NCCL-id path), slab
+world_size 2: rendezvous from the environment, byte broadcast / all-gather (the mailbox-handle path), slab
 ownership / partition / gather, max-over-ranks reductions.  The GPU step itself is replaced by
 the oracle here, so what is checked is that slabs + migration of ownership + gather reproduce
 the single-domain result."""
@@ -44,9 +44,12 @@ WORKER = textwrap.dedent('''
 
     rank, world = cfd.init_process_group("gloo")
     assert world == 2 and dist.get_backend() == "gloo"
-    # 1. byte broadcast (path of the NCCL unique id)
+    # 1. byte broadcast, and the all-gather that carries the mailbox IPC handles to the ring neighbours
     blob = bytes(range(128)) if rank == 0 else None
     assert cfd.broadcast_bytes(blob, 128, 0) == bytes(range(128))
+    handles = cfd.all_gather_bytes(bytes([rank]) * 64)
+    assert handles == [bytes([0]) * 64, bytes([1]) * 64]
+    assert handles[(rank - 1) % world] == handles[(rank + 1) % world] == bytes([1 - rank]) * 64
     # 2. reductions used by bench.py (max over ranks of the step time, sums of counters)
     assert cfd.all_reduce_max(1.0 + rank) == 2.0 and cfd.all_reduce_sum(1.0 + rank) == 3.0
     # 3. slabs: partition -> step -> ownership moves with x -> gather == single-domain oracle

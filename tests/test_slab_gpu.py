@@ -1,5 +1,5 @@
 """Slab-decomposition path on GPUs.  world == 1 runs the complete slab pipeline (class sort,
-ghost layers, seam shift) with device-local copies instead of NCCL; the multi-rank test
+ghost layers, seam shift, mailbox protocol) with the rank's own mailbox as both neighbours; the multi-rank test
 launches tests/dist_check.py under torch.distributed.run when the box has >= 2 GPUs."""
 import os
 import subprocess
@@ -23,7 +23,7 @@ def slab_sim(p, table, radio, state, counts, capacity=None, **opts):
     sim.setForceTable(table)
     for k, v in opts.items():
         sim.setOption(k, v)
-    sim.commInit(0, 1, None, capacity or int(len(state) * 1.2) + 1024)
+    sim.commInit(0, 1, capacity or int(len(state) * 1.2) + 1024)
     sim.uploadOwned(state, counts, np.arange(len(state), dtype=np.int32))
     return sim
 
@@ -83,7 +83,7 @@ def test_slab_global_init_matches_oracle():
     p, table, radio = U.config("eater")
     sim = cf.ParticleSimulation(0, 6, init=False)
     sim.params = U.to_lib_params(p)
-    sim.commInit(0, 1, None, 60000)
+    sim.commInit(0, 1, 60000)
     sim.initParticlesGlobal(50000, 0x5EED0005, cf.INIT_UNIFORM)
     got, _ = by_id(sim, 50000)
     assert got.tobytes() == O.init_particles(50000, 6, 0x5EED0005, 1, p.canvas).tobytes()
