@@ -74,3 +74,24 @@ extern "C" int cf_bench_flush_l2(int device, size_t bytes) {
     flush_kernel<<<1184, 256>>>(g_flush, n, v);
     return cudaDeviceSynchronize() == cudaSuccess ? CF_OK : CF_ERR_CUDA;
 }
+
+// Declared in engine.cu: the stream and device of a handle (bench helper only).
+extern "C" int cf_internal_stream(cf_sim* sim, cudaStream_t* stream, int* device);
+extern "C" int cf_bench_flush_l2_async(cf_sim* sim, size_t bytes) {
+    cudaStream_t st = nullptr;
+    int device = 0;
+    if (cf_internal_stream(sim, &st, &device) != CF_OK) return CF_ERR_ARG;
+    if (cudaSetDevice(device) != cudaSuccess) return CF_ERR_CUDA;
+    size_t n = bytes / sizeof(float4);
+    if (n > g_flush_n) {
+        cudaDeviceSynchronize();
+        cudaFree(g_flush);
+        g_flush = nullptr;
+        if (cudaMalloc(&g_flush, n * sizeof(float4)) != cudaSuccess) return CF_ERR_CUDA;
+        g_flush_n = n;
+    }
+    static float v = 0.f;
+    v += 1.0f;
+    flush_kernel<<<1184, 256, 0, st>>>(g_flush, n, v);
+    return cudaGetLastError() == cudaSuccess ? CF_OK : CF_ERR_CUDA;
+}

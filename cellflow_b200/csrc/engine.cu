@@ -95,6 +95,8 @@ struct cf_sim {
     int ncell = 0;
     bool sorted_valid = false;
 
+    bool graph_count_pending = false; // the last build's edge count / occupancy have not been read back yet
+    int graph_plan_count = 0;
     int2* edges = nullptr;
     int2* edge_slots = nullptr;
     int edge_cap = 0;
@@ -165,7 +167,7 @@ struct cf_sim {
     double wait_timeout_ms = 20000.0;
     double cell_edge = 1.0;        // cell edge and largest interaction radius of the current grid
     float rmax = 0.f;
-    double ms_exchange = 0;
+    double ms_exchange = 0, ms_exchange_mig = 0, ms_exchange_halo = 0;
 
     // CUDA graphs of the (static) single-GPU step sequence: small problems are launch-bound
     struct StepGraph {
@@ -188,8 +190,8 @@ struct cf_sim {
     // stats
     std::vector<StepEvents> ev_pool;
     size_t ev_used = 0;
-    cudaEvent_t ev_g0 = nullptr, ev_g1 = nullptr;
-    bool graph_timed = false;
+    std::vector<cudaEvent_t> gev_pool; // event pairs of the graph builds since the last fold (builds may be asynchronous)
+    size_t gev_used = 0;
     double ms_sort = 0, ms_force = 0, ms_integrate = 0, ms_total = 0, ms_graph = 0, ms_graph_total = 0;
     long long graph_builds = 0;
     long long stat_steps = 0;
@@ -645,8 +647,6 @@ extern "C" int cf_create(int particle_count, int num_types, int device, cf_sim**
         if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) s->sm_count = prop.multiProcessorCount;
     }
     if (rc == 0 && cudaMalloc(&s->d_accum, sizeof(unsigned long long)) != cudaSuccess) rc = fail(CF_ERR_CUDA, "cudaMalloc");
-    if (rc == 0 && cudaEventCreate(&s->ev_g0) != cudaSuccess) rc = fail(CF_ERR_CUDA, "cudaEventCreate");
-    if (rc == 0 && cudaEventCreate(&s->ev_g1) != cudaSuccess) rc = fail(CF_ERR_CUDA, "cudaEventCreate");
     if (rc != 0) {
         cf_destroy(s);
         return rc;
@@ -691,8 +691,7 @@ extern "C" int cf_destroy(cf_sim* s) {
     cudaFree(s->h_start);
     for (auto& ev : s->ev_pool)
         for (int i = 0; i < CF_STEP_EVENTS; i++) cudaEventDestroy(ev.e[i]);
-    if (s->ev_g0) cudaEventDestroy(s->ev_g0);
-    if (s->ev_g1) cudaEventDestroy(s->ev_g1);
+    for (cudaEvent_t e : s->gev_pool) cudaEventDestroy(e);
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
     return CF_OK;
@@ -1297,14 +1296,39 @@ extern "C" int cf_step_host(cf_sim* s, const cf_params* p, const cf_particle* in
 // The graph events of the previous build have completed (every build ends with a stream
 // synchronisation): fold them into the totals before the pair of events is reused.
 static void fold_graph_timing(cf_sim* s) {
-    if (!s->graph_timed) return;
-    float g = 0;
-    if (cudaEventElapsedTime(&g, s->ev_g0, s->ev_g1) == cudaSuccess) {
-        s->ms_graph = g;
-        s->ms_graph_total += g;
-        s->graph_builds++;
+    size_t kept = 0;
+    for (size_t i = 0; i + 1 < s->gev_used; i += 2) {
+        float g = 0;
+        cudaError_t e = cudaEventElapsedTime(&g, s->gev_pool[i], s->gev_pool[i + 1]);
+        if (e == cudaSuccess) {
+            s->ms_graph = g;
+            s->ms_graph_total += g;
+            s->graph_builds++;
+        } else if (e == cudaErrorNotReady) { // an asynchronous build still in flight: keep its pair for later
+            std::swap(s->gev_pool[kept], s->gev_pool[i]);
+            std::swap(s->gev_pool[kept + 1], s->gev_pool[i + 1]);
+            kept += 2;
+        }
     }
-    s->graph_timed = false;
+    (void)cudaGetLastError();
+    s->gev_used = kept;
+}
+// A pair of events for the build being enqueued (nullptr when the pool cannot grow).
+static cudaEvent_t* next_graph_events(cf_sim* s) {
+    if (s->gev_used + 2 > s->gev_pool.size()) {
+        if (s->gev_pool.size() >= 8192) return nullptr;
+        cudaEvent_t a, b;
+        if (cudaEventCreate(&a) != cudaSuccess) return nullptr;
+        if (cudaEventCreate(&b) != cudaSuccess) {
+            cudaEventDestroy(a);
+            return nullptr;
+        }
+        s->gev_pool.push_back(a);
+        s->gev_pool.push_back(b);
+    }
+    cudaEvent_t* p = &s->gev_pool[s->gev_used];
+    s->gev_used += 2;
+    return p;
 }
 
 // Everything cf_build_graph launches depends on this plan (plus the buffers and the step constants).
@@ -1494,8 +1518,8 @@ static int graph_sequence_cached(cf_sim* s, const GraphPlan& P) {
 }
 
 extern "C" int cf_build_graph(cf_sim* s, float dist, int max_conn, int* n_edges) {
-    ARG(s && n_edges);
-    *n_edges = 0;
+    ARG(s);
+    if (n_edges) *n_edges = 0;
     ARG(max_conn >= 0);
     if (int rc = set_device(s)) return rc;
     int mc = std::min(max_conn, CF_MAX_GRAPH_CONN);
@@ -1515,7 +1539,8 @@ extern "C" int cf_build_graph(cf_sim* s, float dist, int max_conn, int* n_edges)
         s->edge_cap = (int)need;
     }
     fold_graph_timing(s);
-    if (s->opt_timing) CU(cudaEventRecord(s->ev_g0, s->stream));
+    cudaEvent_t* gev = s->opt_timing ? next_graph_events(s) : nullptr;
+    if (gev) CU(cudaEventRecord(gev[0], s->stream));
     GraphPlan P;
     if (s->slab) {
         // the cell-list build migrates particles (and synchronises with the host): plan afterwards
@@ -1529,22 +1554,40 @@ extern "C" int cf_build_graph(cf_sim* s, float dist, int max_conn, int* n_edges)
         if (int rc = s->opt_graphs ? graph_sequence_cached(s, P) : graph_device_sequence(s, P, true)) return rc;
     }
     s->last_graph_kernel = P.gkernel;
-    if (s->opt_timing) {
-        CU(cudaEventRecord(s->ev_g1, s->stream));
-        s->graph_timed = true;
+    if (gev) CU(cudaEventRecord(gev[1], s->stream));
+    s->graph_count_pending = true;
+    s->graph_plan_count = s->slab ? std::max(s->n, 1) : P.count;
+    if (!n_edges) { // asynchronous: nothing is read back now
+        CU(cudaGetLastError());
+        return CF_OK;
     }
-    CU(cudaMemcpyAsync(&s->h_graph_occ, s->d_graph_occ, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->stream));
-    CU(cudaMemcpyAsync(&s->n_edges, s->d_edge_count, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
-    CU(cudaStreamSynchronize(s->stream));
-    CU(cudaGetLastError());
-    if (P.count > 0 && s->n > 0) s->graph_mean_occ = (double)s->h_graph_occ / (double)P.count;
-    refresh_policy(s);
+    return cf_get_graph_edge_count(s, n_edges);
+}
+
+extern "C" int cf_get_graph_edge_count(cf_sim* s, int* n_edges) {
+    ARG(s && n_edges);
+    if (int rc = set_device(s)) return rc;
+    if (s->graph_count_pending) {
+        CU(cudaMemcpyAsync(&s->h_graph_occ, s->d_graph_occ, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->stream));
+        CU(cudaMemcpyAsync(&s->n_edges, s->d_edge_count, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+        CU(cudaStreamSynchronize(s->stream));
+        CU(cudaGetLastError());
+        s->graph_count_pending = false;
+        if (int rc = slab_refresh(s)) return rc;
+        if (s->graph_plan_count > 0 && s->n > 0) s->graph_mean_occ = (double)s->h_graph_occ / (double)s->graph_plan_count;
+        refresh_policy(s);
+    }
     *n_edges = s->n_edges;
     return CF_OK;
 }
 
 extern "C" int cf_download_graph_edges(cf_sim* s, cf_edge* edges, int capacity) {
-    ARG(s && (edges || s->n_edges == 0));
+    ARG(s);
+    if (s->graph_count_pending) {
+        int ne = 0;
+        if (int rc = cf_get_graph_edge_count(s, &ne)) return rc;
+    }
+    ARG(edges || s->n_edges == 0);
     ARG(capacity >= s->n_edges);
     if (int rc = set_device(s)) return rc;
     if (s->n_edges == 0) return CF_OK;
@@ -1555,7 +1598,12 @@ extern "C" int cf_download_graph_edges(cf_sim* s, cf_edge* edges, int capacity) 
 
 extern "C" int cf_download_graph_vertices(cf_sim* s, const cf_color* colors, int num_colors, float* vertices,
                                           int capacity_edges) {
-    ARG(s && colors && num_colors >= s->T && (vertices || s->n_edges == 0));
+    ARG(s);
+    if (s->graph_count_pending) {
+        int ne = 0;
+        if (int rc = cf_get_graph_edge_count(s, &ne)) return rc;
+    }
+    ARG(colors && num_colors >= s->T && (vertices || s->n_edges == 0));
     ARG(capacity_edges >= s->n_edges);
     if (int rc = set_device(s)) return rc;
     if (s->n_edges == 0) return CF_OK;
@@ -1599,6 +1647,14 @@ extern "C" int cf_apply_preset(cf_sim* s, const cf_preset* pr) {
 // ---------------------------------------------------------------------------------------------
 // introspection
 // ---------------------------------------------------------------------------------------------
+// bench_util.cu enqueues its L2 flush on the handle's stream (not part of the public header)
+extern "C" int cf_internal_stream(cf_sim* s, cudaStream_t* stream, int* device) {
+    ARG(s && stream && device);
+    *stream = s->stream;
+    *device = s->device;
+    return CF_OK;
+}
+
 extern "C" int cf_set_option(cf_sim* s, const char* name, double value) {
     ARG(s && name);
     std::string k(name);
@@ -1623,11 +1679,12 @@ extern "C" int cf_stats_reset(cf_sim* s) {
     CU(cudaStreamSynchronize(s->stream));
     s->ev_used = 0;
     s->ms_sort = s->ms_force = s->ms_integrate = s->ms_total = s->ms_graph = s->ms_exchange = 0;
+    s->ms_exchange_mig = s->ms_exchange_halo = 0;
     s->ms_graph_total = 0;
     s->graph_builds = 0;
     s->stat_steps = 0;
     s->launches = 0;
-    s->graph_timed = false;
+    s->gev_used = 0;
     return CF_OK;
 }
 
@@ -1648,8 +1705,11 @@ extern "C" int cf_get_stats(cf_sim* s, cf_stats* st) {
         if (ev.has_exchange) { // the two mailbox exchanges: wait + append arrivals, halo pack + wait + ghosts
             float x = 0, y = 0;
             if (cudaEventElapsedTime(&x, ev.e[4], ev.e[5]) == cudaSuccess &&
-                cudaEventElapsedTime(&y, ev.e[6], ev.e[7]) == cudaSuccess)
+                cudaEventElapsedTime(&y, ev.e[6], ev.e[7]) == cudaSuccess) {
                 s->ms_exchange += x + y;
+                s->ms_exchange_mig += x;
+                s->ms_exchange_halo += y;
+            }
         }
         s->ms_total += a + b + c;
         s->stat_steps++;
@@ -1663,6 +1723,8 @@ extern "C" int cf_get_stats(cf_sim* s, cf_stats* st) {
     st->ms_integrate = s->ms_integrate;
     st->ms_graph = s->ms_graph;
     st->ms_exchange = s->ms_exchange;
+    st->ms_exchange_migrants = s->ms_exchange_mig;
+    st->ms_exchange_halo = s->ms_exchange_halo;
     st->steps = s->stat_steps;
     st->launches = s->launches;
     for (int a = 0; a < 3; a++) st->grid[a] = s->sc.dims[a];

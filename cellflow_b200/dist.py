@@ -184,119 +184,3 @@ def make_slab_sim(params, raw, radio, n_total, seed, mode, capacity_factor=1.5, 
     if seed is not None:
         sim.initParticlesGlobal(n_total, seed, mode)
     return sim, rank, world
-
-
-def bench_multi(args, workloads, workload_setup):
-    """bench.py body for world > 1: weak scaling, n_per_gpu particles per rank, one 8000-wide block
-    of canvas per rank along x.  Device-timed per rank (CUDA events inside the library), max over
-    ranks, rank 0 prints the JSON line."""
-    import torch
-
-    from bench import METRIC, ClockSampler  # the script's own helpers
-
-    rank, world = init_process_group("nccl")
-    _, _, local = env_rank()
-    torch.cuda.set_device(local)
-    L = _lib.lib()
-    params, raw, radio, n_total, seed, mode, graph = workload_setup(args.workload, world)
-    sim, rank, world = make_slab_sim(params, raw, radio, n_total, seed, mode)
-    if args.force_kernel:
-        sim.setOption("force_kernel", args.force_kernel)
-    sim.setOption("timing", 1)
-
-    def one_step():
-        sim.simulate(sync=False)
-        if graph:
-            sim.generateProximityGraph(graph[0], graph[1])
-
-    for _ in range(args.warmup):
-        one_step()
-    sim.sync()
-    sim.statsReset()
-    barrier()
-    torch.cuda.synchronize()
-    with ClockSampler(local) as clocks:
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            _lib.check(L.cf_bench_flush_l2(C.c_int(local), C.c_size_t(256 << 20)))
-            one_step()
-            sim.sync()
-        torch.cuda.synchronize()
-        barrier()
-        wall = time.perf_counter() - t0
-        st = sim.stats()
-        graph_ms = st.ms_graph_total  # accumulated inside the library: no per-step stats call (it synchronises)
-    my_ms = st.ms_total / max(st.steps, 1) + graph_ms / args.steps
-    step_ms = all_reduce_max(my_ms)
-    owned = all_reduce_sum(float(st.n_owned))
-    accepted = all_reduce_sum(float(st.accepted_pairs))
-    exch_ms = all_reduce_max(st.ms_exchange / max(st.steps, 1))
-    force_ms = all_reduce_max(st.ms_force / max(st.steps, 1))
-    launches = all_reduce_sum(float(st.launches))
-    tf = C.c_double(0)
-    mhz = C.c_double(0)
-    _lib.check(L.cf_bench_fp32_peak(C.c_int(local), C.byref(tf), C.byref(mhz)))
-
-    # e2e: every rank round-trips what it owns through PINNED host memory each step
-    # (D2H particles+counts+ids -> H2D the same -> step), raw C-ABI calls on the pinned buffers
-    cap = int(st.n_owned * 1.2) + 4096
-    pin_p = torch.empty(cap * 44, dtype=torch.uint8).pin_memory()
-    pin_c = torch.zeros(cap, dtype=torch.int32).pin_memory()
-    pin_i = torch.zeros(cap, dtype=torch.int32).pin_memory()
-    cnt = C.c_int(0)
-
-    def round_trip():
-        _lib.check(L.cf_download_particles_ids(sim._h, C.c_void_p(pin_p.data_ptr()), C.c_void_p(pin_c.data_ptr()),
-                                               C.c_void_p(pin_i.data_ptr()), C.c_int(cap), C.byref(cnt)))
-        _lib.check(L.cf_upload_particles_ids(sim._h, C.c_void_p(pin_p.data_ptr()), C.c_void_p(pin_c.data_ptr()),
-                                             C.c_void_p(pin_i.data_ptr()), cnt))
-        return cnt.value
-
-    e2e_steps = max(3, min(args.steps, 8))
-    round_trip()
-    one_step()
-    sim.sync()
-    barrier()
-    t0 = time.perf_counter()
-    h2d = d2h = 0
-    for _ in range(e2e_steps):
-        m = round_trip()
-        one_step()
-        sim.sync()
-        h2d += m * 52
-        d2h += m * 52
-    barrier()
-    e2e_s = all_reduce_max((time.perf_counter() - t0) / e2e_steps)
-    h2d = all_reduce_sum(h2d / e2e_steps)
-    d2h = all_reduce_sum(d2h / e2e_steps)
-    if rank == 0:
-        out = {
-            "metric": METRIC, "value": round(n_total / (step_ms * 1e-3), 1), "unit": METRIC, "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(step_ms, 4),
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic",
-            "config": {"workload": args.workload, "particles": n_total, "particles_per_gpu": n_total // world,
-                       "types": params.numParticleTypes,
-                       "canvas": [params.canvasWidth, params.canvasHeight, params.canvasDepth],
-                       "radius": params.radius, "ratio": params.ratioWithLFO,
-                       "mean_neighbours": round(accepted / max(owned, 1), 1),
-                       "graph": list(graph) if graph else None,
-                       "l2": "flushed between timed steps (256 MiB overwrite)",
-                       "parallelism": f"{world} x-slabs, peer-to-peer mailbox halo+migration exchange per step (NVLink stores, no collective)",
-                       "timing": "CUDA events per rank, max over ranks"},
-            "e2e": {"value": round(n_total / e2e_s, 1), "unit": METRIC, "h2d_bytes_per_step": int(h2d),
-                    "d2h_bytes_per_step": int(d2h), "ms_per_step": round(e2e_s * 1e3, 4),
-                    "api": "cf_download_particles_ids -> cf_upload_particles_ids -> cf_step per rank, pinned host buffers"},
-            "gpu_launches": int(launches), "clocks": clocks.summary(),
-            "roofline": {"kernel": "pair_force", "bound": "fp32",
-                         "achieved": round(37.0 * accepted / (force_ms * 1e-3) * 1e-12, 3) if force_ms > 0 else None,
-                         "peak": round(tf.value * world, 2), "unit": "TFLOP/s",
-                         "frac": round(37.0 * accepted / (force_ms * 1e-3) * 1e-12 / (tf.value * world), 4)
-                         if force_ms > 0 else None, "traffic": None,
-                         "peak_source": "FFMA microbenchmark on rank 0 x n_gpus"},
-            "phases_ms": {"pair_force_max": round(force_ms, 4), "exchange_max": round(exch_ms, 4)},
-            "cpu_baseline": None, "wall_s_timed_region": round(wall, 3),
-        }
-        print(json.dumps(out), flush=True)
-    sim.close()
-    barrier()

@@ -168,6 +168,16 @@ class ParticleSimulation:
         radio = np.ascontiguousarray(radio, dtype=np.float32)
         check(self._L.cf_set_radio_by_type(self._h, _p(radio), C.c_int(len(radio))))
 
+    def buildGraphAsync(self, proximityDistance: float, maxConnectionsPerParticle: int):
+        """The graph build enqueued without reading anything back (multi-GPU step loops)."""
+        check(self._L.cf_set_params(self._h, C.byref(self.params)))
+        check(self._L.cf_build_graph(self._h, C.c_float(proximityDistance), C.c_int(maxConnectionsPerParticle), None))
+
+    def graphEdgeCount(self) -> int:
+        ne = C.c_int(0)
+        check(self._L.cf_get_graph_edge_count(self._h, C.byref(ne)))
+        return ne.value
+
     def generateProximityGraph(self, proximityDistance: float, maxConnectionsPerParticle: int,
                                particleColors=None):
         """generateProximityGraph(...), .cu:625-687.  Returns (edges, vertices): `edges` is the

@@ -129,6 +129,10 @@ typedef struct cf_stats {
     int32_t graph_kernel;  /* kernel of the last cf_build_graph: 1 thread per particle, 2 warp per particle */
     double ms_graph_total; /* all cf_build_graph calls since cf_stats_reset (timing != 0) */
     int64_t graph_builds;  /* ... and how many they were */
+    double ms_exchange_migrants; /* slab mode, part of ms_exchange: wait for + append the arrivals */
+    double ms_exchange_halo;     /* slab mode, part of ms_exchange: halo pack + wait + ghost unpack + ghost bounds */
+    int64_t exact_tested_pairs;  /* tile kernel, option "count_blocks": pairs that reached the exact per-pair test */
+    int64_t evaluated_pair_lanes;/* tile kernel, option "count_blocks": pair-lanes whose force terms were evaluated */
 } cf_stats;
 
 typedef struct cf_sim cf_sim;
@@ -213,6 +217,9 @@ float cf_ratio_with_lfo(const cf_params* params, float t_seconds);
 /* Builds the edge set on the device; *n_edges receives the edge count (vertexCount/2 of the
  * reference).  max_conn is clamped to CF_MAX_GRAPH_CONN. */
 int cf_build_graph(cf_sim* sim, float proximity_distance, int max_conn, int* n_edges);
+/* n_edges == NULL: asynchronous build (nothing is read back; the step loop of a multi-GPU run never stops for
+ * the host).  cf_get_graph_edge_count synchronises and returns the count of the last build. */
+int cf_get_graph_edge_count(cf_sim* sim, int* n_edges);
 int cf_download_graph_edges(cf_sim* sim, cf_edge* edges, int capacity);
 /* Reference VBO layout: per edge 2 vertices x (pos xyz + colour rgb of i's type) = 12 floats
  * (ParticleSimulation.cu:255-275). */
@@ -284,6 +291,8 @@ int cf_set_option(cf_sim* sim, const char* name, double value);
  * overwrites `bytes` of scratch (> L2 size) between timed iterations. */
 int cf_bench_fp32_peak(int device, double* tflops, double* sm_mhz_effective);
 int cf_bench_flush_l2(int device, size_t bytes);
+/* The same flush enqueued on the handle's stream without synchronising (free-running multi-GPU step loops). */
+int cf_bench_flush_l2_async(cf_sim* sim, size_t bytes);
 const char* cf_last_error(void);
 const char* cf_version(void);
 

@@ -16,8 +16,8 @@ for wl in ${WORKLOADS:-c3-eater-1M c3-pulser-1M c5-settings-2M}; do
     lib=""
     case "$v" in LIB=*) lib="${v%% *}"; lib="${lib#LIB=}"; v="${v#LIB=* }"; [ "$v" = "LIB=$lib" ] && v="";; esac
     [ -n "$lib" ] && export CELLFLOW_B200_LIB=$PWD/cellflow_b200/lib/$lib || unset CELLFLOW_B200_LIB
-    timeout 600 python bench.py --steps ${STEPS:-10} --warmup 3 --no-cpu --workload $wl $v > $out 2> ${out%.json}.err
-    tail -1 $out | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('$wl [$v]', d['ms_per_step'], d['phases_ms'], 'frac', d['roofline']['frac'], 'e2e', d['e2e']['value'], 'nbrs', d['config']['mean_neighbours'])" || tail -5 ${out%.json}.err
+    timeout 600 python bench.py --steps ${STEPS:-10} --warmup 3 --no-cpu --no-extra --workload $wl $v > $out 2> ${out%.json}.err
+    tail -1 $out | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('$wl [$v]', d['ms_per_step'], d['phases_ms'], 'frac', d['roofline']['frac'], 'e2e', d['e2e']['value'], 'nbrs', d['details']['mean_neighbours'], d.get('parity'), d['roofline'].get('block_counters'))" || tail -5 ${out%.json}.err
     vi=$((vi+1))
   done
 done
