@@ -163,7 +163,8 @@ class ClockSampler:
     REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
                0x4: "sw_power_cap", 0x80: "hw_power_brake"}
 
-    def __init__(self, index):
+    def __init__(self, index, period=0.05):
+        self.period = float(os.environ.get("CF_BENCH_CLOCK_PERIOD", period))
         self.samples, self.reasons, self.max_mhz = [], set(), None
         self._stop = threading.Event()
         self._t = None
@@ -186,7 +187,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            self._stop.wait(0.05)
+            self._stop.wait(self.period)
 
     def __enter__(self):
         if self.nv:
@@ -512,7 +513,8 @@ def measure_multi(spec, args, steps, warmup, with_e2e):
         if graph:
             sim.buildGraphAsync(graph[0], graph[1])
 
-    for _ in range(warmup):
+    for _ in range(warmup):  # (the flush allocates its scratch on first use: not inside the timed region)
+        _lib.check(L.cf_bench_flush_l2_async(sim._h, C.c_size_t(L2_FLUSH)))
         one_step()
     sim.sync()
     sim.statsReset()
@@ -539,7 +541,12 @@ def measure_multi(spec, args, steps, warmup, with_e2e):
         force_ms=cfd.all_reduce_max(st.ms_force / k), sort_ms=cfd.all_reduce_max(st.ms_sort / k),
         integ_ms=cfd.all_reduce_max(st.ms_integrate / k), graph_ms=cfd.all_reduce_max(graph_ms / steps),
         launches=cfd.all_reduce_sum(float(st.launches)), ghosts=cfd.all_reduce_sum(float(st.n_ghost)),
-        wall=wall, clocks=clocks.summary(), wall_ms_per_step=cfd.all_reduce_max(wall / steps * 1e3))
+        wall=wall, clocks=clocks.summary(), wall_ms_per_step=cfd.all_reduce_max(wall / steps * 1e3),
+        per_rank=[json.loads(b.decode()) for b in cfd.all_gather_bytes(json.dumps(
+            {"step": round(my_ms, 4), "force": round(st.ms_force / k, 4), "sort": round(st.ms_sort / k, 4),
+             "wait_migrants": round(st.ms_exchange_migrants / k, 4), "wait_halo": round(st.ms_exchange_halo / k, 4),
+             "integrate": round(st.ms_integrate / k, 4), "graph": round(graph_ms / steps, 4),
+             "sm_mhz": clocks.summary()["sm_mhz"], "reasons": clocks.summary()["reasons"]}).encode())])
     if with_e2e:
         # e2e: every rank round-trips what it owns through PINNED host memory each step
         # (D2H particles+counts+ids -> H2D the same -> step), raw C-ABI calls on the pinned buffers
@@ -604,6 +611,7 @@ def run_multi(args):
                                              "integrate_max": round(x["integ_ms"], 4), "graph_max": round(x["graph_ms"], 4),
                                              "exchange_max": round(x["exch_ms"], 4)},
                                "owned_max_over_mean": round(x["owned_max"] * world / max(x["owned"], 1), 3),
+                               "per_rank_ms": x["per_rank"],
                                "mean_neighbours": round(x["accepted"] / max(x["owned"], 1), 1)}
             except Exception as e:
                 extra[name] = {"error": str(e)[:300]}
@@ -621,7 +629,7 @@ def run_multi(args):
                         "owned_max_over_mean": round(r["owned_max"] * world / max(r["owned"], 1), 3),
                         "ghost_particles": int(r["ghosts"]), "timing": "CUDA events per rank and step, max over ranks; "
                         "free-running step loop (one host synchronisation after the K timed steps)",
-                        "wall_ms_per_step": round(r["wall_ms_per_step"], 4)},
+                        "wall_ms_per_step": round(r["wall_ms_per_step"], 4), "per_rank_ms": r["per_rank"]},
             "e2e": {"value": round(n_total / r["e2e_s"], 1), "unit": METRIC, "h2d_bytes_per_step": int(r["h2d"]),
                     "d2h_bytes_per_step": int(r["d2h"]), "ms_per_step": round(r["e2e_s"] * 1e3, 4), "steps": r["e2e_steps"],
                     "api": "cf_download_particles_ids -> cf_upload_particles_ids -> cf_step per rank, pinned host buffers"},

@@ -508,7 +508,10 @@ static int prepare_step_const(cf_sim* s) {
 template <class KeyFn, bool GEN>
 static int radix_sort_run(cf_sim* s, KeyFn fn, uint32_t* k[2], uint32_t* v[2], int n_upper, const int* dn,
                           long long key_range, int* out_src) {
-    const RsPlan P = rs_make_plan(n_upper, key_range);
+    // block shape from the EXPECTED count (slab mode launches over capacities; the real count is a device word)
+    long long expect = n_upper;
+    if (dn && s->slab) expect = std::min<long long>(n_upper, (s->n_total > 0 ? s->n_total / s->world : s->cap_own) * 5 / 4 + 4096);
+    const RsPlan P = rs_make_plan(n_upper, key_range, (int)expect);
     const size_t hist_need = (size_t)RS_MAX_BINS * P.nblocks + RS_MAX_BINS;
     if (hist_need > s->hist_cap) {
         CU(cudaStreamSynchronize(s->stream));
@@ -1005,7 +1008,8 @@ static int build_homog_copy(cf_sim* s) {
     // slab mode: every slot up to the end of the right ghost layer, a count only the device knows
     // (cell_start[ncell]); slots before the left ghost layer hold nothing and get the sentinel key
     const int nslots = s->slab ? s->cap : s->n;
-    const int* d_nslots = s->slab ? s->cell_start + s->ncell : nullptr;
+    const int* d_nslots = s->slab ? s->d_slab + SLAB_NSLOTS : nullptr;
+    const int* d_first = s->slab ? s->d_slab + SLAB_FIRST : nullptr;
     const int nkeys = nrow * s->T * nz; // composite keys (row * T + type) * nz + cz
     if ((size_t)nslots > s->homog_cap) {
         CU(cudaStreamSynchronize(s->stream));
@@ -1036,7 +1040,7 @@ static int build_homog_copy(cf_sim* s) {
     }
     const float4* pos = s->pos[s->cur];
     LAUNCH(s, homog_key_kernel, div_up(nslots, 256), 256, 0, pos, s->cell_start, s->ncell, nz, s->T, nslots, d_nslots,
-           s->hk[0], s->hv[0], s->h_cell_of);
+           d_first, s->hk[0], s->hv[0], s->h_cell_of);
     int src = 0;
     if (int rc = radix_sort_pairs(s, s->hk, s->hv, nslots, (long long)nrow * s->T + 1, &src, d_nslots)) return rc;
     LAUNCH(s, homog_gather_kernel, div_up(nslots, 256), 256, 0, s->hk[src], s->hv[src], pos, s->h_cell_of, nz, nslots,
@@ -1148,7 +1152,7 @@ static int step_direct(cf_sim* s, StepEvents* ev) {
     if (s->slab) {
         // fused integrate + migrant emission: the leavers go straight into the neighbours' mailboxes
         s->seq_mig++;
-        LAUNCH(s, integrate_slab_kernel, div_up(s->cap_own, 256), 256, 0, opos(s), ovel(s), ofrc(s), oid(s), s->cap_own, s->sc,
+        LAUNCH(s, integrate_slab_kernel, slab_grid(s), 256, 0, opos(s), ovel(s), ofrc(s), oid(s), s->cap_own, s->sc,
                s->geom, slab_peers(s), s->seq_mig);
         s->mig_sent = true;
     } else if (s->n > 0) {
@@ -1433,9 +1437,10 @@ static int graph_device_sequence(cf_sim* s, const GraphPlan& P, bool with_cell_l
     if (!(P.count > 0 && (s->n > 0 || s->slab))) return 0;
     const int count = P.count, nkeys = P.nkeys;
     // slab mode: slots [0, cell_start[ncell]) take part and the owned count is a device word
-    const int* d_n = s->slab ? s->cell_start + s->ncell : nullptr;
+    const int* d_n = s->slab ? s->d_slab + SLAB_NSLOTS : nullptr;
+    const int* d_first = s->slab ? s->d_slab + SLAB_FIRST : nullptr;
     const int* d_own = s->slab ? s->d_slab + SLAB_NCUR : nullptr;
-    LAUNCH(s, graph_key_kernel, div_up(count, 256), 256, 0, s->pos[s->cur], P.first, count, d_n, P.g, s->cell_start, s->ncell,
+    LAUNCH(s, graph_key_kernel, div_up(count, 256), 256, 0, s->pos[s->cur], P.first, d_first, count, d_n, P.g, s->cell_start, s->ncell,
            s->base, s->n, d_own, P.use_lo_ghost, P.use_hi_ghost, s->gk[0], s->gv[0]);
     int src = 0;
     if (int rc = radix_sort_pairs(s, s->gk, s->gv, count, (long long)nkeys + 1, &src, d_n)) return rc;

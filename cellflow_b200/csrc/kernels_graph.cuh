@@ -37,12 +37,14 @@ __device__ __forceinline__ int graph_coord(float x, float org, float inv, int n)
 // extents are read from the cell list on the device (cell_start[0], cell_start[ncell]), so the
 // host never has to wait for the ghost counts.
 // Slab mode: the slot count (d_n) and the owned count (d_own_n) are read on the device.
-__global__ void graph_key_kernel(const float4* __restrict__ pos4, int first, int n_upper, const int* __restrict__ d_n,
+__global__ void graph_key_kernel(const float4* __restrict__ pos4, int first_host, const int* __restrict__ d_first,
+                                 int n_upper, const int* __restrict__ d_n,
                                  GraphGrid g, const int* __restrict__ cell_start, int ncell, int own_first, int own_n_host,
                                  const int* __restrict__ d_own_n, int use_lo_ghost, int use_hi_ghost,
                                  uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
     const int n = d_n ? min(*d_n, n_upper) : n_upper;
     const int own_n = d_own_n ? *d_own_n : own_n_host;
+    const int first = d_first ? *d_first : first_host;
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     const int slot = first + k;

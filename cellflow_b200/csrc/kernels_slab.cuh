@@ -37,7 +37,10 @@
 
 // device status / count words
 enum { SLAB_NCUR = 0, SLAB_NTMP = 1, SLAB_ERR = 2, SLAB_GHOST_L = 4, SLAB_GHOST_R = 5, SLAB_SEND_L = 6, SLAB_SEND_R = 7,
-       SLAB_TICKET_MIG = 8, SLAB_TICKET_HALO = 9, SLAB_ARR_L = 10, SLAB_ARR_R = 11, SLAB_WORDS = 32 };
+       SLAB_TICKET_MIG = 8, SLAB_TICKET_HALO = 9, SLAB_ARR_L = 10, SLAB_ARR_R = 11,
+       SLAB_FIRST = 12,  // first used slot (start of the left ghost layer)
+       SLAB_NSLOTS = 13, // used slots: left ghosts + owned + right ghosts
+       SLAB_WORDS = 32 };
 
 struct SlabGeom {
     float x_lo, x_hi;       // owned interval (global coordinates), x_hi == right neighbour's x_lo bit for bit
@@ -147,8 +150,7 @@ __device__ __forceinline__ void slab_close_migrants(const SlabPeers& P, int seq)
 __global__ void slab_emit_migrants_kernel(const float4* __restrict__ pos4, const float4* __restrict__ vel4,
                                           const int* __restrict__ id, int n_upper, SlabGeom g, SlabPeers P, int seq) {
     const int n = min(P.status[SLAB_NCUR], n_upper);
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k < n) {
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
         const float4 p = pos4[k];
         const int dir = slab_direction(p.x, g, P.status);
         if (dir) slab_emit_migrant(P, dir, seq & 1, p, vel4[k], id[k]);
@@ -164,8 +166,7 @@ __global__ void integrate_slab_kernel(float4* __restrict__ pos4, float4* __restr
                                       const int* __restrict__ id, int n_upper, StepConst c, SlabGeom g, SlabPeers P,
                                       int seq) {
     const int n = min(P.status[SLAB_NCUR], n_upper);
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k < n) {
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) { // grid sized for the expected count
         float4 p = pos4[k], v = vel4[k], f = frc4[k];
         cf_integrate_particle(p, v, f, c);
         pos4[k] = p;
@@ -272,20 +273,21 @@ slab_unpack_arrivals_kernel(char* __restrict__ mybox, SlabMail mail, int par, fl
 // Layer ranges come from cell_start on the device.
 __global__ void slab_pack_halo_kernel(const float4* __restrict__ pos4, const int* __restrict__ id,
                                       const int* __restrict__ cell_start, int layer_cells, int nxl, SlabPeers P, int seq) {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
     const int l0 = cell_start[layer_cells], l1 = cell_start[2 * layer_cells];
     const int r0 = cell_start[nxl * layer_cells], r1 = cell_start[(nxl + 1) * layer_cells];
     const int cap = P.mail.cap_halo, par = seq & 1;
     const int nl = l1 - l0, nr = r1 - r0;
-    if (k < min(nl, cap)) {
-        char* m = P.mail.halo(P.left, 1, par);
-        P.mail.halo_pos(m)[k] = pos4[l0 + k];
-        P.mail.halo_id(m)[k] = id[l0 + k];
-    }
-    if (k < min(nr, cap)) {
-        char* m = P.mail.halo(P.right, 0, par);
-        P.mail.halo_pos(m)[k] = pos4[r0 + k];
-        P.mail.halo_id(m)[k] = id[r0 + k];
+    char* const ml = P.mail.halo(P.left, 1, par);
+    char* const mr = P.mail.halo(P.right, 0, par);
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < min(max(nl, nr), cap); k += gridDim.x * blockDim.x) {
+        if (k < nl) {
+            P.mail.halo_pos(ml)[k] = pos4[l0 + k];
+            P.mail.halo_id(ml)[k] = id[l0 + k];
+        }
+        if (k < nr) {
+            P.mail.halo_pos(mr)[k] = pos4[r0 + k];
+            P.mail.halo_id(mr)[k] = id[r0 + k];
+        }
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -310,10 +312,10 @@ __global__ void slab_unpack_ghosts_kernel(char* __restrict__ mybox, SlabMail mai
                                           int* __restrict__ id, int own_first, const int* __restrict__ status,
                                           uint32_t* __restrict__ gkeys_left, uint32_t* __restrict__ gkeys_right,
                                           StepConst c) {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
     const int n_own = status[SLAB_NCUR];
     const int nl = min(max(*mail.cnt_halo(mybox, 0, par), 0), mail.cap_halo);
     const int nr = min(max(*mail.cnt_halo(mybox, 1, par), 0), mail.cap_halo);
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < max(nl, nr); k += gridDim.x * blockDim.x) {
     if (k < nl) {
         char* m = mail.halo(mybox, 0, par);
         const float4 p = __ldcg(&mail.halo_pos(m)[k]);
@@ -332,6 +334,7 @@ __global__ void slab_unpack_ghosts_kernel(char* __restrict__ mybox, SlabMail mai
         const int cy = cf_cell_coord(p.y, c.inv[1], c.dims[1]), cz = cf_cell_coord(p.z, c.inv[2], c.dims[2]);
         gkeys_right[k] = (uint32_t)(((c.dims[0] - 1) * c.dims[1] + cy) * c.dims[2] + cz) * CF_KEY_SUB;
     }
+    }
 }
 
 // cell_start of the two ghost layers (lower bounds over the ghost key arrays).
@@ -345,6 +348,8 @@ __global__ void slab_ghost_bounds_kernel(const uint32_t* __restrict__ gkeys_left
     if (k == 0) {
         status[SLAB_GHOST_L] = nl;
         status[SLAB_GHOST_R] = nr;
+        status[SLAB_FIRST] = own_first - nl;
+        status[SLAB_NSLOTS] = nl + n_own + nr;
     }
     if (k < layer_cells) { // cells of layer 0: c = k
         const uint32_t want = (uint32_t)k * CF_KEY_SUB;

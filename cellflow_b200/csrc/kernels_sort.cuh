@@ -214,7 +214,7 @@ rs_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restri
 struct RsPlan {
     int passes, bits_per_pass, R, groups, items, nblocks;
 };
-static inline RsPlan rs_make_plan(int n_upper, long long key_range) {
+static inline RsPlan rs_make_plan(int n_upper, long long key_range, int n_expected) {
     RsPlan p;
     int bits = 1;
     while ((1ll << bits) < key_range) bits++;
@@ -222,11 +222,12 @@ static inline RsPlan rs_make_plan(int n_upper, long long key_range) {
     p.bits_per_pass = (bits + p.passes - 1) / p.passes;
     // items per block = 256 * R * groups: about 4 CTAs per SM for mid-sized inputs, rows of <= 2048 blocks
     const long long target_blocks = 148 * 4;
-    long long per = (n_upper + target_blocks - 1) / target_blocks;
+    if (n_expected <= 0 || n_expected > n_upper) n_expected = n_upper;
+    long long per = (n_expected + target_blocks - 1) / target_blocks;
     int R = 1;
     while (R < 8 && RS_THREADS * R < per) R *= 2;
     int groups = 1;
-    while (((long long)n_upper + (long long)RS_THREADS * R * groups - 1) / ((long long)RS_THREADS * R * groups) > 2048) groups *= 2;
+    while (((long long)n_upper + (long long)RS_THREADS * R * groups - 1) / ((long long)RS_THREADS * R * groups) > 4096) groups *= 2;
     p.R = R;
     p.groups = groups;
     p.items = RS_THREADS * R * groups;

@@ -460,10 +460,13 @@ force_tile4_kernel(const float4* __restrict__ pos4, const int* __restrict__ cell
 // ---------------------------------------------------------------------------------------------
 __global__ void homog_key_kernel(const float4* __restrict__ pos4, const int* __restrict__ cell_start, int ncell,
                                  int nz, int T, int nslots_upper, const int* __restrict__ d_nslots,
-                                 uint32_t* __restrict__ keys, uint32_t* __restrict__ vals, int* __restrict__ cell_of) {
+                                 const int* __restrict__ d_first, uint32_t* __restrict__ keys,
+                                 uint32_t* __restrict__ vals, int* __restrict__ cell_of) {
+    // element e of the copy <-> slot first + e (slab mode: the used slots start at the left ghost layer)
     const int nslots = d_nslots ? min(*d_nslots, nslots_upper) : nslots_upper;
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= nslots) return;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nslots) return;
+    const int k = e + (d_first ? *d_first : 0);
     uint32_t key = (uint32_t)((ncell / nz) * T); // sentinel: slot holds no particle
     int cell = -1;
     if (k >= cell_start[0] && k < cell_start[ncell]) {
@@ -477,8 +480,8 @@ __global__ void homog_key_kernel(const float4* __restrict__ pos4, const int* __r
         t = t < 0 ? 0 : (t > T - 1 ? T - 1 : t);
         key = (uint32_t)((cell / nz) * T + t);
     }
-    keys[k] = key;
-    vals[k] = (uint32_t)k;
+    keys[e] = key;
+    vals[e] = (uint32_t)k;
     cell_of[k] = cell;
 }
 

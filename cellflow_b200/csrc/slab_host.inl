@@ -41,6 +41,13 @@ static void slab_update_geom(cf_sim* s) {
     s->geom.w_right = slab_width(s, s->rank + 1);
 }
 
+// Blocks of 256 threads for a grid-stride walk over the owned particles: sized for the expected count (the
+// global count over the ranks, else the capacity), capped at a few waves of the device.
+static int slab_grid(const cf_sim* s) {
+    const long long expect = s->n_total > 0 ? std::min<long long>(s->cap_own, s->n_total / s->world + 1) : s->cap_own;
+    return (int)std::max<long long>(1, std::min<long long>((expect + 255) / 256, (long long)s->sm_count * 32));
+}
+
 static SlabPeers slab_peers(const cf_sim* s) {
     SlabPeers P;
     P.left = s->peer_box[0];
@@ -89,8 +96,9 @@ extern "C" int cf_comm_init(cf_sim* s, int rank, int world, int capacity) {
     s->world = world;
     s->slab = true;
     s->cap_own = capacity;
-    if (s->cap_halo <= 0) s->cap_halo = std::max(32768, capacity / 4);
-    if (s->cap_mig <= 0) s->cap_mig = std::max(16384, capacity / 16);
+    // a boundary layer can be the whole slab (one or two x layers per rank at 8-way strong scaling)
+    if (s->cap_halo <= 0) s->cap_halo = std::max(32768, capacity);
+    if (s->cap_mig <= 0) s->cap_mig = std::max(16384, capacity / 8);
     s->mail.cap_halo = s->cap_halo;
     s->mail.cap_mig = s->cap_mig;
     s->n = 0;
@@ -166,6 +174,7 @@ static int ensure_sorted_slab(cf_sim* s, cudaEvent_t* ev_x) {
     const int cur = s->cur, nxt = cur ^ 1;
     const int B = s->base;
     const int NU = s->cap_own; // launch bound of everything that walks the owned particles
+    const int gs = slab_grid(s); // grid-stride kernels: blocks for the expected count, not for the capacity
     const long long KC = (long long)s->ncell * CF_KEY_SUB;
     s->geom.class_stride = (uint32_t)KC;
     const SlabPeers P = slab_peers(s);
@@ -173,7 +182,7 @@ static int ensure_sorted_slab(cf_sim* s, cudaEvent_t* ev_x) {
     // ---- migrants: emitted by the previous step's integrate kernel, or here after an upload / spawn / move ----
     if (!s->mig_sent) {
         s->seq_mig++;
-        LAUNCH(s, slab_emit_migrants_kernel, div_up(NU, 256), 256, 0, s->pos[cur] + B, s->vel[cur] + B, s->id[cur] + B, NU,
+        LAUNCH(s, slab_emit_migrants_kernel, gs, 256, 0, s->pos[cur] + B, s->vel[cur] + B, s->id[cur] + B, NU,
                s->geom, P, s->seq_mig);
     }
     s->mig_sent = false;
@@ -199,11 +208,11 @@ static int ensure_sorted_slab(cf_sim* s, cudaEvent_t* ev_x) {
     const int layer_cells = s->sc.dims[1] * s->sc.dims[2];
     s->seq_halo++;
     const int hpar = s->seq_halo & 1;
-    LAUNCH(s, slab_pack_halo_kernel, div_up(s->cap_halo, 256), 256, 0, s->pos[nxt], s->id[nxt], s->cell_start, layer_cells,
+    LAUNCH(s, slab_pack_halo_kernel, std::max(1, gs / 4), 256, 0, s->pos[nxt], s->id[nxt], s->cell_start, layer_cells,
            s->nxl, P, s->seq_halo);
     LAUNCH(s, slab_wait_kernel, 1, 32, 0, s->mail.flag_halo(s->mailbox, 0), s->mail.flag_halo(s->mailbox, 1), s->seq_halo,
            s->d_slab, tmo);
-    LAUNCH(s, slab_unpack_ghosts_kernel, div_up(s->cap_halo, 256), 256, 0, s->mailbox, s->mail, hpar, s->pos[nxt], s->id[nxt],
+    LAUNCH(s, slab_unpack_ghosts_kernel, std::max(1, gs / 4), 256, 0, s->mailbox, s->mail, hpar, s->pos[nxt], s->id[nxt],
            B, s->d_slab, s->gkeys[0], s->gkeys[1], s->sc);
     LAUNCH(s, slab_ghost_bounds_kernel, div_up(2 * layer_cells + 1, 256), 256, 0, s->gkeys[0], s->gkeys[1], s->mailbox, s->mail,
            hpar, s->cell_start, layer_cells, s->ncell, B, s->d_slab);
