@@ -121,9 +121,9 @@ SYMBOLS = [
     "cf_init_particles", "cf_upload_particles", "cf_download_particles",
     "cf_upload_neighbor_counts", "cf_download_neighbor_counts", "cf_render_feed", "cf_move_universe",
     "cf_set_params", "cf_get_params", "cf_step", "cf_sync", "cf_step_host", "cf_ratio_with_lfo",
-    "cf_build_graph", "cf_get_graph_edge_count", "cf_download_graph_edges", "cf_download_graph_vertices",
+    "cf_build_graph", "cf_get_graph_edge_count", "cf_download_graph_edges", "cf_download_graph_vertices", "cf_graph_vertices_device",
     "cf_default_params", "cf_default_preset", "cf_load_preset", "cf_save_preset",
-    "cf_apply_preset", "cf_comm_init", "cf_comm_mailbox_handle", "cf_comm_connect", "cf_slab_set_bounds", "cf_init_particles_global", "cf_slab_bounds",
+    "cf_apply_preset", "cf_save_snapshot", "cf_load_snapshot", "cf_comm_init", "cf_comm_mailbox_handle", "cf_comm_connect", "cf_slab_set_bounds", "cf_init_particles_global", "cf_slab_bounds",
     "cf_upload_particles_ids",
     "cf_download_particles_ids", "cf_get_stats", "cf_stats_reset", "cf_download_cell_keys",
     "cf_set_option", "cf_bench_fp32_peak", "cf_bench_flush_l2", "cf_bench_flush_l2_async", "cf_last_error", "cf_version",

@@ -78,6 +78,7 @@ struct cf_sim {
     float force[CF_TT_MAX];
     float half_host[CF_T_MAX];
     bool force_overridden = false;
+    struct GlibcRand* rng = nullptr; // the handle's own copy of libc's never-seeded rand() stream (.cu:513-539)
 
     float4* pos[2] = {nullptr, nullptr};
     float4* vel[2] = {nullptr, nullptr};
@@ -94,7 +95,12 @@ struct cf_sim {
     StepConst sc;
     int ncell = 0;
     bool sorted_valid = false;
+    unsigned long long state_gen = 1;   // bumped by every reorder and every change of positions
+    unsigned long long graph_gen = 0;   // state_gen at the end of the last graph build: its edge slots are valid while equal
 
+    float* d_vertices = nullptr;      // persistent vertex stream of the last graph (12 floats per edge)
+    size_t vertex_cap = 0;            // ... in edges
+    float* d_colors = nullptr;
     bool graph_count_pending = false; // the last build's edge count / occupancy have not been read back yet
     int graph_plan_count = 0;
     int2* edges = nullptr;
@@ -184,6 +190,9 @@ struct cf_sim {
     // options
     int opt_force_kernel = 0; // 0 auto, 1 per-particle, 2 tile (generation 3), 3 tile (generation 4)
     int opt_timing = 0;
+    int opt_count_blocks = 0; // instrumented tile kernel: counts exact-tested / evaluated blocks (cf_stats)
+    unsigned long long* d_block_counts = nullptr;
+    bool block_counts_valid = false;
     int opt_t4_ctas = 0;      // experiment: resident CTAs per SM of the generation-4 tile kernel (0 = default 5)
     double opt_max_cells_per_particle = 16.0; // fine grids pay off for clustered states (cells are cheap)
 
@@ -265,7 +274,7 @@ static int alloc_particle_buffers(cf_sim* s, int cap) {
     CU(cudaMemsetAsync(s->frc, 0, c * sizeof(float4), s->stream));
     s->cap = (int)c;
     s->cur = 0;
-    s->sorted_valid = false;
+    s->sorted_valid = false, s->state_gen++;
     return 0;
 }
 
@@ -303,7 +312,10 @@ struct GlibcRand {
         k = 344;
     }
     int next() {
-        if (k >= 344 + 4096) k = 344; // never reached by the table draws
+        if (k >= 344 + 4096) { // keep the last 34 values and continue (a handle may regenerate tables for ever)
+            for (int i = 0; i < 34; i++) r[310 + i] = r[k - 34 + i];
+            k = 344;
+        }
         r[k] = (int32_t)((uint32_t)r[k - 31] + (uint32_t)r[k - 3]);
         int out = (int)(((uint32_t)r[k]) >> 1);
         k++;
@@ -485,7 +497,7 @@ static int prepare_step_const(cf_sim* s) {
                         memcmp(c.W, s->sc.W, sizeof(c.W)) != 0;
     s->sc = c;
     s->ncell = (int)ncell;
-    if (grid_changed) s->sorted_valid = false;
+    if (grid_changed) s->sorted_valid = false, s->state_gen++;
     if ((size_t)ncell + 1 > s->cell_cap) {
         cudaFree(s->cell_start);
         s->cell_start = nullptr;
@@ -568,7 +580,7 @@ static int ensure_sorted(cf_sim* s) {
            s->ncell, 0, nullptr);
     if (src != 0) std::swap(s->keys[0], s->keys[1]), std::swap(s->vals[0], s->vals[1]);
     // keys[0] now holds the sorted keys of the current order
-    s->cur = nxt;
+    s->cur = nxt, s->state_gen++;
     s->sorted_valid = true;
     CU(cudaGetLastError());
     return 0;
@@ -650,12 +662,13 @@ extern "C" int cf_create(int particle_count, int num_types, int device, cf_sim**
         if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) s->sm_count = prop.multiProcessorCount;
     }
     if (rc == 0 && cudaMalloc(&s->d_accum, sizeof(unsigned long long)) != cudaSuccess) rc = fail(CF_ERR_CUDA, "cudaMalloc");
+    if (rc == 0 && cudaMalloc(&s->d_block_counts, 2 * sizeof(unsigned long long)) != cudaSuccess) rc = fail(CF_ERR_CUDA, "cudaMalloc");
     if (rc != 0) {
         cf_destroy(s);
         return rc;
     }
-    GlibcRand g;
-    default_tables(s, g);
+    s->rng = new GlibcRand();
+    default_tables(s, *s->rng);
     *out = s;
     return CF_OK;
 }
@@ -675,7 +688,10 @@ extern "C" int cf_destroy(cf_sim* s) {
     cudaFree(s->d_tables);
     cudaFree(s->d_edge_count);
     cudaFree(s->d_graph_occ);
+    cudaFree(s->d_vertices);
+    cudaFree(s->d_colors);
     cudaFree(s->d_accum);
+    cudaFree(s->d_block_counts);
     cudaFree(s->d_tiles);
     for (int b = 0; b < 2; b++) cudaFree(s->gk[b]), cudaFree(s->gv[b]);
     cudaFree(s->gpos);
@@ -696,6 +712,7 @@ extern "C" int cf_destroy(cf_sim* s) {
         for (int i = 0; i < CF_STEP_EVENTS; i++) cudaEventDestroy(ev.e[i]);
     for (cudaEvent_t e : s->gev_pool) cudaEventDestroy(e);
     if (s->stream) cudaStreamDestroy(s->stream);
+    delete s->rng;
     delete s;
     return CF_OK;
 }
@@ -728,8 +745,8 @@ extern "C" int cf_set_num_particle_types(cf_sim* s, int types) {
     ARG(s && types >= 1 && types <= CF_MAX_PARTICLE_TYPES);
     s->T = types;
     s->params.numParticleTypes = types;
-    GlibcRand g;
-    default_tables(s, g);
+    // successive table draws continue ONE sequence, like the reference process's rand() (.cu:574-579)
+    default_tables(s, *s->rng);
     return cf_init_particles(s, 0x5EED0000ull, CF_INIT_SPAWN_CUBE);
 }
 
@@ -738,7 +755,7 @@ extern "C" int cf_set_num_particle_types(cf_sim* s, int types) {
 // ---------------------------------------------------------------------------------------------
 extern "C" int cf_regenerate_force_table(cf_sim* s) {
     ARG(s);
-    static thread_local GlibcRand g; // successive calls continue the sequence like rand() would
+    GlibcRand& g = *s->rng; // successive calls continue the construction draws, like rand() would
     for (int i = 0; i < s->T * s->T; i++) s->raw[i] = (float)g.next() / 2147483647 * 2.0f - 1.0f;
     squash_force_table(s, 0.28f, -0.20f, 1.0f);
     return CF_OK;
@@ -807,7 +824,7 @@ extern "C" int cf_init_particles(cf_sim* s, uint64_t seed, int mode) {
         LAUNCH(s, init_particles_kernel, div_up(s->n, 256), 256, 0, opos(s), ovel(s), ofrc(s),
                oid(s), s->n, 0, s->T, seed, mode, s->params.canvasWidth, s->params.canvasHeight,
                s->params.canvasDepth);
-    s->sorted_valid = false;
+    s->sorted_valid = false, s->state_gen++;
     CU(cudaGetLastError());
     return CF_OK;
 }
@@ -853,8 +870,8 @@ static int upload_impl(cf_sim* s, const cf_particle* aos, const int32_t* counts,
         CU(cudaMemcpyAsync(d_ids, ids, sizeof(int) * (size_t)count, cudaMemcpyHostToDevice, s->stream));
     }
     LAUNCH(s, aos_to_soa_kernel, div_up(count, 256), 256, 0, s->d_aos, counts ? s->d_counts : nullptr, d_ids,
-           opos(s), ovel(s), ofrc(s), oid(s), count);
-    s->sorted_valid = false;
+           opos(s), ovel(s), ofrc(s), oid(s), count, s->T);
+    s->sorted_valid = false, s->state_gen++;
     CU(cudaGetLastError());
     return CF_OK;
 }
@@ -959,7 +976,7 @@ extern "C" int cf_move_universe(cf_sim* s, float dx, float dy, float dz) {
     // the reference passes the DEFAULT canvas here (.cu:586-589); the engine uses the live one
     LAUNCH(s, move_universe_kernel, div_up(s->n, 256), 256, 0, opos(s), s->n, dx, dy, dz,
            s->params.canvasWidth, s->params.canvasHeight, s->params.canvasDepth);
-    s->sorted_valid = false;
+    s->sorted_valid = false, s->state_gen++;
     CU(cudaGetLastError());
     return CF_OK;
 }
@@ -1110,15 +1127,26 @@ static int launch_force(cf_sim* s) {
             const int grid = s->sm_count * ctas;
             const size_t pad = ctas < T4_MINB ? (size_t)(220 * 1024 / ctas) - 36 * 1024 : 0;
             if (pad) {
-                cudaFuncSetAttribute(force_tile4_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad);
-                cudaFuncSetAttribute(force_tile4_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad);
+                cudaFuncSetAttribute(force_tile4_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad);
+                cudaFuncSetAttribute(force_tile4_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad);
+            }
+            if (s->opt_count_blocks) { // instrumented build: exact-tested and evaluated (layer, quad) blocks
+                CU(cudaMemsetAsync(s->d_block_counts, 0, 2 * sizeof(unsigned long long), s->stream));
+                if (homog)
+                    LAUNCH(s, (force_tile4_kernel<1, true>), grid, T4_WARPS * 32, pad, pos, s->cell_start, s->h_pos, s->h_start,
+                           s->d_tiles, s->d_tile_ctrl, s->frc, s->sc, s->d_tables, s->d_block_counts);
+                else
+                    LAUNCH(s, (force_tile4_kernel<0, true>), grid, T4_WARPS * 32, pad, pos, s->cell_start, pos, s->cell_start,
+                           s->d_tiles, s->d_tile_ctrl, s->frc, s->sc, s->d_tables, s->d_block_counts);
+                s->block_counts_valid = true;
+                return 0;
             }
             if (homog)
-                LAUNCH(s, force_tile4_kernel<1>, grid, T4_WARPS * 32, pad, pos, s->cell_start, s->h_pos, s->h_start,
-                       s->d_tiles, s->d_tile_ctrl, s->frc, s->sc, s->d_tables);
+                LAUNCH(s, (force_tile4_kernel<1, false>), grid, T4_WARPS * 32, pad, pos, s->cell_start, s->h_pos, s->h_start,
+                       s->d_tiles, s->d_tile_ctrl, s->frc, s->sc, s->d_tables, nullptr);
             else
-                LAUNCH(s, force_tile4_kernel<0>, grid, T4_WARPS * 32, pad, pos, s->cell_start, pos, s->cell_start,
-                       s->d_tiles, s->d_tile_ctrl, s->frc, s->sc, s->d_tables);
+                LAUNCH(s, (force_tile4_kernel<0, false>), grid, T4_WARPS * 32, pad, pos, s->cell_start, pos, s->cell_start,
+                       s->d_tiles, s->d_tile_ctrl, s->frc, s->sc, s->d_tables, nullptr);
             return 0;
         }
         const int grid = s->sm_count * 4;
@@ -1159,7 +1187,7 @@ static int step_direct(cf_sim* s, StepEvents* ev) {
         LAUNCH(s, integrate_kernel, div_up(s->n, 256), 256, 0, opos(s), ovel(s), ofrc(s), s->n, s->sc);
     }
     if (ev) CU(cudaEventRecord(ev->e[3], s->stream));
-    s->sorted_valid = false;
+    s->sorted_valid = false, s->state_gen++;
     return 0;
 }
 
@@ -1173,7 +1201,7 @@ static std::vector<char> step_signature(const cf_sim* s) {
                           s->h_comp, s->h_start};
     put(ptrs, sizeof(ptrs));
     int ints[] = {s->n, s->ncell, s->cur, s->opt_force_kernel, s->sorted_valid ? 1 : 0, s->half_bound_ok ? 1 : 0,
-                  s->planned_force_kernel, s->opt_t4_ctas};
+                  s->planned_force_kernel, s->opt_t4_ctas, s->opt_count_blocks};
     put(ints, sizeof(ints));
     return sig;
 }
@@ -1202,9 +1230,9 @@ static int step_graphed(cf_sim* s, StepEvents* ev) {
         if (ev) CU(cudaEventRecord(ev->e[3], s->stream));
         if (!s->sorted_valid) { // what ensure_sorted does on the host
             if (hit->swap_keys) std::swap(s->keys[0], s->keys[1]), std::swap(s->vals[0], s->vals[1]);
-            s->cur ^= 1;
+            s->cur ^= 1, s->state_gen++;
         }
-        s->sorted_valid = false;
+        s->sorted_valid = false, s->state_gen++;
         s->launches += hit->nodes;
         return 0;
     }
@@ -1482,7 +1510,7 @@ static int graph_sequence_cached(cf_sim* s, const GraphPlan& P) {
         CU(cudaGraphLaunch(hit->exec, s->stream));
         if (!was_sorted) { // what ensure_sorted does on the host
             if (hit->swap_keys) std::swap(s->keys[0], s->keys[1]), std::swap(s->vals[0], s->vals[1]);
-            s->cur ^= 1;
+            s->cur ^= 1, s->state_gen++;
         }
         s->sorted_valid = true;
         s->launches += hit->nodes;
@@ -1560,6 +1588,7 @@ extern "C" int cf_build_graph(cf_sim* s, float dist, int max_conn, int* n_edges)
     }
     s->last_graph_kernel = P.gkernel;
     if (gev) CU(cudaEventRecord(gev[1], s->stream));
+    s->graph_gen = s->state_gen;
     s->graph_count_pending = true;
     s->graph_plan_count = s->slab ? std::max(s->n, 1) : P.count;
     if (!n_edges) { // asynchronous: nothing is read back now
@@ -1601,33 +1630,137 @@ extern "C" int cf_download_graph_edges(cf_sim* s, cf_edge* edges, int capacity) 
     return CF_OK;
 }
 
-extern "C" int cf_download_graph_vertices(cf_sim* s, const cf_color* colors, int num_colors, float* vertices,
-                                          int capacity_edges) {
+// Vertex stream of the last graph (reference VBO layout, .cu:248-276) written on the device: into memory the
+// caller owns (device_dst: e.g. the mapped pointer of the widget's VBO, CellFlowWidget.cpp:606-617 — zero copy),
+// or into the library's persistent buffer.  Asynchronous on the handle's stream.
+extern "C" int cf_graph_vertices_device(cf_sim* s, const cf_color* colors, int num_colors, float* device_dst,
+                                        int capacity_edges, const float** device_ptr) {
     ARG(s);
+    if (device_ptr) *device_ptr = nullptr;
+    if (int rc = set_device(s)) return rc;
     if (s->graph_count_pending) {
         int ne = 0;
         if (int rc = cf_get_graph_edge_count(s, &ne)) return rc;
     }
-    ARG(colors && num_colors >= s->T && (vertices || s->n_edges == 0));
-    ARG(capacity_edges >= s->n_edges);
-    if (int rc = set_device(s)) return rc;
+    ARG(colors && num_colors >= s->T);
     if (s->n_edges == 0) return CF_OK;
-    if (!s->sorted_valid) return fail(CF_ERR_STATE, "graph vertices requested after the particles moved");
-    float* d_colors = nullptr;
-    float* d_out = nullptr;
-    CU(cudaMalloc(&d_colors, sizeof(float) * 3 * (size_t)num_colors));
-    if (cudaMalloc(&d_out, sizeof(float) * 12 * (size_t)s->n_edges) != cudaSuccess) {
-        cudaFree(d_colors);
-        return fail(CF_ERR_CUDA, "cudaMalloc vertices");
+    // edge slots refer to the particle order the graph was built on: any later reorder or move invalidates them
+    if (s->graph_gen != s->state_gen)
+        return fail(CF_ERR_STATE, "graph vertices requested after the particles moved or were reordered: build the graph again");
+    float* out = device_dst;
+    if (out) {
+        ARG(capacity_edges >= s->n_edges);
+    } else {
+        if ((size_t)s->n_edges > s->vertex_cap) {
+            CU(cudaStreamSynchronize(s->stream));
+            cudaFree(s->d_vertices);
+            s->d_vertices = nullptr;
+            s->vertex_cap = (size_t)s->n_edges + (size_t)s->n_edges / 4 + 1024;
+            CU(cudaMalloc(&s->d_vertices, sizeof(float) * 12 * s->vertex_cap));
+        }
+        out = s->d_vertices;
     }
-    cudaMemcpyAsync(d_colors, colors, sizeof(float) * 3 * (size_t)num_colors, cudaMemcpyHostToDevice, s->stream);
-    LAUNCH(s, graph_vertices_kernel, div_up(s->n_edges, 256), 256, 0, s->edge_slots, s->n_edges, s->pos[s->cur],
-           d_colors, s->T, d_out);
-    cudaMemcpyAsync(vertices, d_out, sizeof(float) * 12 * (size_t)s->n_edges, cudaMemcpyDeviceToHost, s->stream);
-    cudaError_t e = cudaStreamSynchronize(s->stream);
-    cudaFree(d_colors);
-    cudaFree(d_out);
-    if (e != cudaSuccess) return fail(CF_ERR_CUDA, "graph vertices: %s", cudaGetErrorString(e));
+    if (!s->d_colors) CU(cudaMalloc(&s->d_colors, sizeof(float) * 3 * CF_T_MAX));
+    CU(cudaMemcpyAsync(s->d_colors, colors, sizeof(float) * 3 * (size_t)std::min(num_colors, CF_T_MAX), cudaMemcpyHostToDevice,
+                       s->stream));
+    LAUNCH(s, graph_vertices_kernel, div_up(s->n_edges, 256), 256, 0, s->edge_slots, s->n_edges, s->pos[s->cur], s->d_colors,
+           s->T, out);
+    CU(cudaGetLastError());
+    if (device_ptr) *device_ptr = out;
+    return CF_OK;
+}
+
+extern "C" int cf_download_graph_vertices(cf_sim* s, const cf_color* colors, int num_colors, float* vertices,
+                                          int capacity_edges) {
+    ARG(s);
+    const float* dev = nullptr;
+    if (int rc = cf_graph_vertices_device(s, colors, num_colors, nullptr, 0, &dev)) return rc;
+    if (s->n_edges == 0) return CF_OK;
+    ARG(vertices && capacity_edges >= s->n_edges);
+    CU(cudaMemcpyAsync(vertices, dev, sizeof(float) * 12 * (size_t)s->n_edges, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    return CF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// particle snapshot (no reference counterpart: savePreset persists parameters only,
+// CellFlowWidget.cpp:1182-1269; the snapshot is what makes a run — and a parity failure — reproducible)
+// ---------------------------------------------------------------------------------------------
+struct SnapshotHeader {
+    char magic[8]; // "CFSNAP02"
+    uint32_t header_bytes;
+    int32_t n, T;
+    cf_params params;
+    float raw[CF_TT_MAX], radio[CF_T_MAX], force[CF_TT_MAX];
+    int32_t force_overridden;
+    int32_t rank, world;
+    int32_t reserved[5];
+};
+
+extern "C" int cf_save_snapshot(cf_sim* s, const char* path) {
+    ARG(s && path);
+    if (int rc = set_device(s)) return rc;
+    if (int rc = slab_refresh(s)) return rc;
+    const int n = s->n;
+    std::vector<cf_particle> aos((size_t)std::max(n, 1));
+    std::vector<int32_t> counts((size_t)std::max(n, 1)), ids((size_t)std::max(n, 1));
+    int got = 0;
+    // slot order + ids: a restored run sorts the same input order, so it continues bit for bit
+    if (int rc = cf_download_particles_ids(s, aos.data(), counts.data(), ids.data(), std::max(n, 1), &got)) return rc;
+    SnapshotHeader h;
+    memset(&h, 0, sizeof(h));
+    memcpy(h.magic, "CFSNAP02", 8);
+    h.header_bytes = (uint32_t)sizeof(h);
+    h.n = got;
+    h.T = s->T;
+    h.params = s->params;
+    memcpy(h.raw, s->raw, sizeof(h.raw));
+    memcpy(h.radio, s->radio, sizeof(h.radio));
+    memcpy(h.force, s->force, sizeof(h.force));
+    h.force_overridden = s->force_overridden ? 1 : 0;
+    h.rank = s->rank, h.world = s->world;
+    FILE* f = fopen(path, "wb");
+    if (!f) return fail(CF_ERR_IO, "cannot write snapshot %s", path);
+    bool ok = fwrite(&h, sizeof(h), 1, f) == 1;
+    if (got > 0) {
+        ok = ok && fwrite(aos.data(), sizeof(cf_particle), (size_t)got, f) == (size_t)got;
+        ok = ok && fwrite(counts.data(), sizeof(int32_t), (size_t)got, f) == (size_t)got;
+        ok = ok && fwrite(ids.data(), sizeof(int32_t), (size_t)got, f) == (size_t)got;
+    }
+    ok = (fclose(f) == 0) && ok;
+    if (!ok) return fail(CF_ERR_IO, "short write to snapshot %s", path);
+    return CF_OK;
+}
+
+extern "C" int cf_load_snapshot(cf_sim* s, const char* path) {
+    ARG(s && path);
+    if (int rc = set_device(s)) return rc;
+    FILE* f = fopen(path, "rb");
+    if (!f) return fail(CF_ERR_IO, "cannot read snapshot %s", path);
+    SnapshotHeader h;
+    bool ok = fread(&h, sizeof(h), 1, f) == 1 && memcmp(h.magic, "CFSNAP02", 8) == 0 && h.header_bytes == sizeof(h) &&
+              h.n >= 0 && h.T >= 1 && h.T <= CF_MAX_PARTICLE_TYPES;
+    std::vector<cf_particle> aos;
+    std::vector<int32_t> counts, ids;
+    if (ok && h.n > 0) {
+        aos.resize((size_t)h.n), counts.resize((size_t)h.n), ids.resize((size_t)h.n);
+        ok = fread(aos.data(), sizeof(cf_particle), (size_t)h.n, f) == (size_t)h.n &&
+             fread(counts.data(), sizeof(int32_t), (size_t)h.n, f) == (size_t)h.n &&
+             fread(ids.data(), sizeof(int32_t), (size_t)h.n, f) == (size_t)h.n;
+    }
+    fclose(f);
+    if (!ok) return fail(CF_ERR_IO, "%s is not a cellflow_b200 snapshot (or is truncated)", path);
+    if (s->slab && (h.rank != s->rank || h.world != s->world))
+        return fail(CF_ERR_ARG, "snapshot of rank %d/%d loaded into rank %d/%d", h.rank, h.world, s->rank, s->world);
+    s->T = h.T;
+    s->params = h.params;
+    s->params.numParticleTypes = h.T;
+    memcpy(s->raw, h.raw, sizeof(h.raw));
+    memcpy(s->radio, h.radio, sizeof(h.radio));
+    memcpy(s->force, h.force, sizeof(h.force));
+    s->force_overridden = h.force_overridden != 0;
+    if (int rc = upload_impl(s, aos.data(), counts.data(), ids.data(), h.n)) return rc;
+    CU(cudaStreamSynchronize(s->stream)); // the staging vectors go out of scope
     return CF_OK;
 }
 
@@ -1667,6 +1800,7 @@ extern "C" int cf_set_option(cf_sim* s, const char* name, double value) {
     else if (k == "graph_kernel") s->opt_graph_kernel = (int)value; // 0 auto, 1 thread per particle, 2 warp per particle
     else if (k == "timing") s->opt_timing = (int)value;
     else if (k == "t4_ctas_per_sm") s->opt_t4_ctas = (int)value;
+    else if (k == "count_blocks") s->opt_count_blocks = (int)value, s->block_counts_valid = false;
     else if (k == "max_cells_per_particle") s->opt_max_cells_per_particle = value;
     else if (k == "cuda_graphs") s->opt_graphs = (int)value;
     else if (k == "global_particle_count") s->n_total = (long long)value; // same value on every rank
@@ -1674,7 +1808,7 @@ extern "C" int cf_set_option(cf_sim* s, const char* name, double value) {
     else if (k == "migrant_capacity") s->cap_mig = (int)value;     // before cf_comm_init, same on every rank
     else if (k == "wait_timeout_ms") s->wait_timeout_ms = value;
     else return fail(CF_ERR_ARG, "unknown option '%s'", name);
-    s->sorted_valid = false;
+    s->sorted_valid = false, s->state_gen++;
     return CF_OK;
 }
 
@@ -1741,6 +1875,13 @@ extern "C" int cf_get_stats(cf_sim* s, cf_stats* st) {
     st->ms_graph_total = s->ms_graph_total;
     st->graph_builds = s->graph_builds;
     if (s->slab) st->n_ghost = s->h_slab[SLAB_GHOST_L] + s->h_slab[SLAB_GHOST_R];
+    if (s->block_counts_valid) { // (layer of 32 i, quad of 4 j) blocks of the last instrumented force pass
+        unsigned long long bc[2] = {0, 0};
+        CU(cudaMemcpyAsync(bc, s->d_block_counts, sizeof(bc), cudaMemcpyDeviceToHost, s->stream));
+        CU(cudaStreamSynchronize(s->stream));
+        st->exact_tested_pairs = (long long)bc[0] * 128;
+        st->evaluated_pair_lanes = (long long)bc[1] * 128;
+    }
     if (s->n > 0) {
         unsigned long long acc = 0;
         CU(cudaMemsetAsync(s->d_accum, 0, sizeof(unsigned long long), s->stream));

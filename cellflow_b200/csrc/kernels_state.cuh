@@ -48,11 +48,14 @@ __global__ void init_particles_kernel(float4* __restrict__ pos4, float4* __restr
 __global__ void aos_to_soa_kernel(const AosParticle* __restrict__ aos, const int* __restrict__ counts,
                                   const int* __restrict__ ids, float4* __restrict__ pos4,
                                   float4* __restrict__ vel4, float4* __restrict__ frc4,
-                                  int* __restrict__ id, int n) {
+                                  int* __restrict__ id, int n, int T) {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     AosParticle p = aos[k];
     int c = counts ? counts[k] : 0;
+    // the reference's own spawn can produce ptype == numTypes (curand_uniform may return 1.0, .cu:62), which
+    // indexes its tables out of bounds; here every kernel's tables are sized T, so the type is clamped on entry
+    p.ptype = p.ptype < (uint32_t)T ? p.ptype : (uint32_t)(T - 1);
     pos4[k] = make_float4(p.pos[0], p.pos[1], p.pos[2], __uint_as_float(p.ptype));
     vel4[k] = make_float4(p.vel[0], p.vel[1], p.vel[2], __int_as_float(c));
     frc4[k] = make_float4(p.acc[0], p.acc[1], p.acc[2], __int_as_float(c));

@@ -139,12 +139,13 @@ __device__ __forceinline__ void t4_live(u64 dxa, u64 dya, u64 dza, u64 d2a, u64 
 // All live (layer, quad) blocks of one staged chunk.  MODE 0 takes the uniform threshold and derives
 // the table address from the packed types; MODE 1 reads (c2, A, B, cut2) of (layer, lane) from
 // shared memory per block.
-template <int MODE, bool WRAP>
+template <int MODE, bool WRAP, bool COUNT>
 __device__ __forceinline__ void t4_chunk(unsigned sbase, const unsigned (&live)[TK_IPT], const float (&npx)[TK_IPT],
                                          const float (&npy)[TK_IPT], const float (&npz)[TK_IPT], unsigned tis4,
                                          unsigned s_tab_addr, unsigned cst_addr, float sx, float sy,
                                          float sz, float cutu, float c2u, float pau, float pbu,
-                                         T4AccScalar (&acc)[TK_IPT], int (&cnt)[TK_IPT]) {
+                                         T4AccScalar (&acc)[TK_IPT], int (&cnt)[TK_IPT], unsigned& n_tested,
+                                         unsigned& n_live) {
     const u64 sx2 = tk_pack(sx, sx), sy2 = tk_pack(sy, sy), sz2 = tk_pack(sz, sz);
     constexpr unsigned STRIDE = T4_WARPS * 2 * T4_JC * 4; // bytes between the x, y, z, t arrays
     // live[k] bit q = (quad q, layer k) passed the box prefilter; quads with no live layer cost nothing
@@ -188,7 +189,9 @@ __device__ __forceinline__ void t4_chunk(unsigned sbase, const unsigned (&live)[
             tk_unpack(d2a, a0, a1);
             tk_unpack(d2b, b0, b1);
             const float mn = fminf(fminf(a0, a1), fminf(b0, b1));
+            if (COUNT) n_tested++; // instrumented build (option "count_blocks"): (layer, quad) blocks exact-tested
             if (__any_sync(0xffffffffu, mn < cs.w)) {
+                if (COUNT) n_live++; // ... and blocks whose 128 pair-lanes are evaluated
                 const unsigned fva = s_tab_addr + ((tis4 >> (8 * k)) & 255u);
                 t4_live<MODE>(dxa, dya, dza, d2a, dxb, dyb, dzb, d2b, a0, a1, b0, b1, cs.w, cs.x, cs.y, cs.z, fva, Tq,
                               acc[k], cnt[k]);
@@ -197,12 +200,12 @@ __device__ __forceinline__ void t4_chunk(unsigned sbase, const unsigned (&live)[
     }
 }
 
-template <int MODE>
+template <int MODE, bool COUNT = false>
 __global__ void __launch_bounds__(T4_WARPS * 32, T4_MINB)
 force_tile4_kernel(const float4* __restrict__ pos4, const int* __restrict__ cell_start,
                    const float4* __restrict__ posj, const int* __restrict__ startj,
                    const int2* __restrict__ tiles, int* __restrict__ ctrl, float4* __restrict__ frc4, StepConst c,
-                   const DeviceTables* __restrict__ tables) {
+                   const DeviceTables* __restrict__ tables, unsigned long long* __restrict__ block_counts = nullptr) {
     __shared__ __align__(16) T4Shared<MODE> sm;
     // MODE 0: s_tab[tj*T + ti] = fv.  MODE 1: s_tab4[tj*T + ti] = (c2, fv*rep, -fv*att/Reff, cut2)
     __shared__ __align__(16) float s_tab[CF_TT_MAX * (MODE ? 4 : 1)];
@@ -246,6 +249,7 @@ force_tile4_kernel(const float4* __restrict__ pos4, const int* __restrict__ cell
         split = (c2 < c1 && c2 <= c4) ? 2 : ((c4 < c1 && c4 < c2) ? 4 : 1);
     }
     const int nvirtual = full + tail * split;
+    unsigned n_tested = 0, n_live = 0;
 
     for (;;) {
         int tile = 0;
@@ -429,11 +433,11 @@ force_tile4_kernel(const float4* __restrict__ pos4, const int* __restrict__ cell
             }
             if (live[0] | live[1] | live[2] | live[3]) {
                 if (wrap)
-                    t4_chunk<MODE, true>(sbase, live, npx, npy, npz, tis4, s_tab_addr, cst_addr, sx, sy, sz, cutu, c2u, pau, pbu,
-                                         acc, cnt);
+                    t4_chunk<MODE, true, COUNT>(sbase, live, npx, npy, npz, tis4, s_tab_addr, cst_addr, sx, sy, sz, cutu, c2u,
+                                                pau, pbu, acc, cnt, n_tested, n_live);
                 else
-                    t4_chunk<MODE, false>(sbase, live, npx, npy, npz, tis4, s_tab_addr, cst_addr, sx, sy, sz, cutu, c2u, pau,
-                                          pbu, acc, cnt);
+                    t4_chunk<MODE, false, COUNT>(sbase, live, npx, npy, npz, tis4, s_tab_addr, cst_addr, sx, sy, sz, cutu, c2u,
+                                                 pau, pbu, acc, cnt, n_tested, n_live);
             }
             buf ^= 1; // the other buffer was last read one chunk ago by this same warp
         }
@@ -450,6 +454,10 @@ force_tile4_kernel(const float4* __restrict__ pos4, const int* __restrict__ cell
                 frc4[i_begin + il] = make_float4(f.x, f.y, f.z, __int_as_float(cnt[k] - self_ok));
             }
         }
+    }
+    if (COUNT && lane == 0 && block_counts) {
+        atomicAdd(&block_counts[0], (unsigned long long)n_tested);
+        atomicAdd(&block_counts[1], (unsigned long long)n_live);
     }
 }
 

@@ -162,7 +162,7 @@ extern "C" int cf_slab_set_bounds(cf_sim* s, const float* bounds, int count) {
     ARG(bounds[0] == 0.0f);
     if (s->mig_sent) return fail(CF_ERR_STATE, "cf_slab_set_bounds: a migrant exchange is pending (build the cell list or sync first)");
     s->bounds.assign(bounds, bounds + count);
-    s->sorted_valid = false;
+    s->sorted_valid = false, s->state_gen++;
     return CF_OK;
 }
 
@@ -202,7 +202,7 @@ static int ensure_sorted_slab(cf_sim* s, cudaEvent_t* ev_x) {
            s->pos[cur] + B, s->vel[cur] + B, s->id[cur] + B, s->pos[nxt] + B, s->vel[nxt] + B, s->id[nxt] + B, NU,
            s->d_slab + SLAB_NTMP, s->cell_start, s->ncell, B, s->d_slab + SLAB_NCUR);
     if (src != 0) std::swap(s->keys[0], s->keys[1]), std::swap(s->vals[0], s->vals[1]);
-    s->cur = nxt;
+    s->cur = nxt, s->state_gen++;
     // ---- ghost layers ----
     if (ev_x) CU(cudaEventRecord(ev_x[2], s->stream));
     const int layer_cells = s->sc.dims[1] * s->sc.dims[2];
@@ -282,6 +282,6 @@ static int slab_init_particles(cf_sim* s, long long n_total, uint64_t seed, int 
     for (int b = 0; b < 2; b++) cudaFree(k[b]), cudaFree(v[b]);
     if (rc) return rc;
     if (int rc2 = slab_set_owned_count(s, mine)) return rc2;
-    s->sorted_valid = false;
+    s->sorted_valid = false, s->state_gen++;
     return CF_OK;
 }

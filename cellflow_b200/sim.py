@@ -197,7 +197,30 @@ class ParticleSimulation:
                                                      _p(verts), C.c_int(ne.value)))
         return edges, verts
 
+    def graphVerticesDevice(self, particleColors, device_dst: int = 0, capacity_edges: int = 0) -> int:
+        """The last graph's vertex stream written on the device (zero-copy hand-off to a renderer): into
+        `device_dst` (a device pointer the caller owns, e.g. a mapped GL VBO) or into the library's persistent
+        buffer.  Returns the device address of the stream.  Asynchronous; sync() orders it."""
+        colors = np.ascontiguousarray(particleColors, dtype=COLOR)
+        ptr = C.c_void_p()
+        check(self._L.cf_graph_vertices_device(self._h, _p(colors), C.c_int(len(colors)), C.c_void_p(device_dst or None),
+                                               C.c_int(capacity_edges), C.byref(ptr)))
+        return ptr.value or 0
+
     # -- beyond the reference class ------------------------------------------------------------
+    def saveSnapshot(self, path: str):
+        """Parameters, tables and the full particle state (pos, vel, acc, type, previous count, id)."""
+        import os
+        check(self._L.cf_set_params(self._h, C.byref(self.params)))
+        check(self._L.cf_save_snapshot(self._h, os.fsencode(path)))
+
+    def loadSnapshot(self, path: str):
+        import os
+        check(self._L.cf_load_snapshot(self._h, os.fsencode(path)))
+        p = Params()
+        check(self._L.cf_get_params(self._h, C.byref(p)))
+        self.params = p
+
     def applyPreset(self, preset: Preset):
         """CellFlowWidget::loadPreset applied to the simulation (CellFlowWidget.cpp:1079-1177)."""
         check(self._L.cf_apply_preset(self._h, C.byref(preset)))

@@ -165,6 +165,25 @@ public:
         check(cf_download_graph_vertices(sim_, colors.data(), (int)colors.size(), lineVertices.data(), ne));
         outVertexCount = 2 * ne;
     }
+    // Zero-copy form: the stream is written on the device straight into `mappedVbo`, the pointer the GL side
+    // gets from cudaGraphicsResourceGetMappedPointer for its VBO (what the reference does inside
+    // generateProximityGraph, .cu:633-676) — no host round trip.  capacityEdges = VBO size / 48 bytes.
+    void generateProximityGraphDevice(float* mappedVbo, int capacityEdges, int& outVertexCount, float proximityDistance,
+                                      int maxConnectionsPerParticle, const std::vector<ParticleColor>& particleColors) {
+        int ne = 0;
+        check(cf_build_graph(sim_, proximityDistance, maxConnectionsPerParticle, &ne));
+        std::vector<ParticleColor> colors(particleColors);
+        if ((int)colors.size() < numTypes()) colors.resize((size_t)numTypes(), ParticleColor{1.f, 1.f, 1.f});
+        check(cf_graph_vertices_device(sim_, colors.data(), (int)colors.size(), mappedVbo, capacityEdges, nullptr));
+        check(cf_sync(sim_));
+        outVertexCount = 2 * ne;
+    }
+    // Particle snapshot (beyond the reference, whose savePreset keeps parameters only).
+    void saveSnapshot(const std::string& path) { check(cf_save_snapshot(sim_, path.c_str())); }
+    void loadSnapshot(const std::string& path) {
+        check(cf_load_snapshot(sim_, path.c_str()));
+        pullTables();
+    }
     // Reference signature (.cuh:60-66).  `vboUploader(vbo, data, bytes)` is supplied by the GL side.
     std::function<void(unsigned int, const float*, size_t)> vboUploader;
     void generateProximityGraph(unsigned int openglVBO, int& outVertexCount, float proximityDistance,

@@ -225,6 +225,14 @@ int cf_download_graph_edges(cf_sim* sim, cf_edge* edges, int capacity);
  * (ParticleSimulation.cu:255-275). */
 int cf_download_graph_vertices(cf_sim* sim, const cf_color* colors, int num_colors,
                                float* vertices, int capacity_edges);
+/* Zero-copy hand-off of the same stream (the reference writes it into a mapped GL VBO, .cu:633-676, consumer
+ * CellFlowWidget.cpp:606-617): written on the device into `device_dst` — memory the caller owns, e.g. the
+ * pointer cudaGraphicsResourceGetMappedPointer returns for the widget's VBO — or, with device_dst == NULL, into
+ * a persistent buffer of the library whose address is returned in *device_ptr (valid until the next call).
+ * Asynchronous on the handle's stream; cf_sync() orders it.  CF_ERR_STATE when the particles were moved or
+ * reordered since cf_build_graph. */
+int cf_graph_vertices_device(cf_sim* sim, const cf_color* colors, int num_colors, float* device_dst,
+                             int capacity_edges, const float** device_ptr);
 
 /* ---- presets (CellFlowWidget::loadPreset / savePreset, CellFlowWidget.cpp:1070-1269) ----- */
 
@@ -235,6 +243,15 @@ int cf_save_preset(const char* path, const cf_preset* preset);
 /* Applies a preset the way loadPreset does: count, types, radioByType, rawForceTable, then
  * updateForceTable(forceRange, forceBias, forceOffset) (CellFlowWidget.cpp:1079-1177). */
 int cf_apply_preset(cf_sim* sim, const cf_preset* preset);
+
+/* ---- particle snapshot (new: the reference's savePreset persists parameters only, CellFlowWidget.cpp:1182-1269) ---- */
+
+/* Binary snapshot of everything a run continues from: parameters, tables, and per particle pos / vel / acc / type /
+ * previous neighbour count / id in the engine's current slot order.  A handle restored with cf_load_snapshot
+ * continues bit for bit like the one that wrote the file (same device, same options).  Slab mode: one file per
+ * rank. */
+int cf_save_snapshot(cf_sim* sim, const char* path);
+int cf_load_snapshot(cf_sim* sim, const char* path);
 
 /* ---- multi-GPU slabs (new; no reference counterpart) ---------------- */
 

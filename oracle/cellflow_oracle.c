@@ -140,6 +140,8 @@ typedef struct pair_acc {
                        two terms is NOT a usable scale: it crosses zero inside the radius, and
                        there even the reference's own fp32 arithmetic is off by more than 1e-5 of
                        it (tests/test_oracle.py::test_f64_error_budget). */
+    float fnet_sum; /* sum over accepted pairs of |forceValue * netForce| = sum |f_ij| (SURVEY.md section 7's norm);
+                       reported beside the gross-term norm, not used as the tolerance scale (see above) */
     int count;
 } pair_acc;
 
@@ -165,6 +167,7 @@ static inline int pair_term(const cf_params* P, const float* table, const float*
     acc->fy = fmaf(s, dy / dist, acc->fy);
     acc->fz = fmaf(s, dz / dist, acc->fz);
     acc->fabs_sum += fabsf(fv) * (fabsf(e * P->repulsion) + fabsf(r * P->attraction));
+    acc->fnet_sum += fabsf(s);
     return 1;
 }
 
@@ -198,7 +201,7 @@ void orc_step_bruteforce(const cf_particle* in, const int32_t* cnt_in, int n, co
 #pragma omp parallel for schedule(static) num_threads(nthreads > 0 ? nthreads : 1)
 #endif
     for (int i = 0; i < n; i++) {
-        pair_acc acc = {0.f, 0.f, 0.f, 0.f, 0};
+        pair_acc acc = {0.f, 0.f, 0.f, 0.f, 0.f, 0};
         for (int j = 0; j < n; j++) {
             if (j == i) continue;
             pair_term(P, table, reffT, &in[i], &in[j], &acc);
@@ -328,6 +331,10 @@ void orc_step_cells_range(const cf_particle* in, const int32_t* cnt_in, int n, i
                           const cf_params* P, const float* table, const float* radio,
                           cf_particle* out, int32_t* cnt_out, float* fabs_out, int nthreads);
 
+/* Optional second norm of the next cell-list steps: fnet[i] = sum_j |f_ij| (NULL switches it off). */
+static float* g_fnet_out = NULL;
+void orc_set_fnet_output(float* fnet) { g_fnet_out = fnet; }
+
 void orc_step_cells(const cf_particle* in, const int32_t* cnt_in, int n, const cf_params* P,
                     const float* table, const float* radio, cf_particle* out, int32_t* cnt_out,
                     float* fabs_out, int nthreads) {
@@ -356,7 +363,7 @@ void orc_step_cells_range(const cf_particle* in, const int32_t* cnt_in, int n, i
 #pragma omp for schedule(dynamic, 256)
 #endif
         for (int i = i0; i < i1; i++) {
-            pair_acc acc = {0.f, 0.f, 0.f, 0.f, 0};
+            pair_acc acc = {0.f, 0.f, 0.f, 0.f, 0.f, 0};
             int m = gather_candidates(&g, in, i, W, 1, &buf, &cap);
             for (int q = 0; q < m; q++) {
                 int j = buf[q];
@@ -366,6 +373,7 @@ void orc_step_cells_range(const cf_particle* in, const int32_t* cnt_in, int n, i
             finish_particle(P, &in[i], cnt_in ? cnt_in[i] : 0, &acc, &out[i]);
             cnt_out[i] = acc.count;
             if (fabs_out) fabs_out[i] = acc.fabs_sum;
+            if (g_fnet_out) g_fnet_out[i] = acc.fnet_sum;
         }
         free(buf);
     }

@@ -158,6 +158,19 @@ def step(pin, cnt_in, params: Params, table, radio, method="cells", threads=1):
     return out, cnt, fabs
 
 
+def step_norms(pin, cnt_in, params: Params, table, radio, threads=1):
+    """Cell-list step that also returns fnet[i] = sum_j |f_ij| (the net pair forces' magnitudes): the
+    norm SURVEY.md section 7 names, reported beside the gross-term norm `fabs`."""
+    n = len(pin)
+    fnet = np.zeros(n, dtype=np.float32)
+    lib().orc_set_fnet_output(_p(fnet))
+    try:
+        out, cnt, fabs = step(pin, cnt_in, params, table, radio, "cells", threads)
+    finally:
+        lib().orc_set_fnet_output(None)
+    return out, cnt, fabs, fnet
+
+
 def set_sort_candidates(on: bool):
     lib().orc_set_sort_candidates(C.c_int(1 if on else 0))
 

@@ -137,3 +137,17 @@ def hilbert64(sx, sy, sz):
         for i in range(n):
             h = (h << 1) | ((X[i] >> b) & 1)
     return h.astype(np.uint32)
+
+
+def force_err_report(acc, acc_ref, fabs, fnet, mult):
+    """The force error of one step under three norms (max over particles):
+       gross   |err|_inf / (m * sum_j |fv| (|rep e| + |att r|))   — the tolerance scale (FORCE_RTOL)
+       net     |err|_inf / (m * sum_j |f_ij|)                       — SURVEY.md section 7's norm
+       finf    max_i |err_i|_inf / max_i |F_i|_inf                  — against the largest force of the system"""
+    err = np.abs(acc.astype(np.float64) - acc_ref.astype(np.float64)).max(axis=1)
+    m = np.abs(mult)
+    gross = (err / (m * fabs.astype(np.float64) + 1e-30)).max()
+    has = fnet > 0
+    net = (err[has] / (m[has] * fnet[has].astype(np.float64))).max() if has.any() else 0.0
+    finf = err.max() / max(np.abs(acc_ref.astype(np.float64)).max(), 1e-30)
+    return {"gross": float(gross), "net": float(net), "finf": float(finf)}
