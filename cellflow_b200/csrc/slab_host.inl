@@ -156,11 +156,13 @@ extern "C" int cf_comm_connect(cf_sim* s, const void* left_handle64, const void*
     return CF_OK;
 }
 
+static int slab_drain(cf_sim* s);
 extern "C" int cf_slab_set_bounds(cf_sim* s, const float* bounds, int count) {
     ARG(s && s->slab && bounds && count == s->world + 1);
     for (int r = 0; r < s->world; r++) ARG(bounds[r + 1] > bounds[r]);
     ARG(bounds[0] == 0.0f);
-    if (s->mig_sent) return fail(CF_ERR_STATE, "cf_slab_set_bounds: a migrant exchange is pending (build the cell list or sync first)");
+    if (int rc = set_device(s)) return rc;
+    if (int rc = slab_drain(s)) return rc; // a pending migrant exchange belongs to the old bounds (collective)
     s->bounds.assign(bounds, bounds + count);
     s->sorted_valid = false, s->state_gen++;
     return CF_OK;

@@ -51,19 +51,64 @@ def slab_bound(width: float, r: int, world: int) -> np.float32:
     return np.float32(np.float64(np.float32(width)) * np.float64(r) / np.float64(world))
 
 
-def slab_owner(x: np.ndarray, width: float, world: int) -> np.ndarray:
+def slab_bounds_array(width: float, world: int, bounds=None) -> np.ndarray:
+    """The world + 1 slab bounds: the uniform split (same expression as the C library) or explicit ones."""
+    if bounds is not None:
+        b = np.asarray(bounds, dtype=np.float32)
+        assert len(b) == world + 1
+        return b
+    return np.array([slab_bound(width, r, world) for r in range(world + 1)], dtype=np.float32)
+
+
+def slab_owner(x: np.ndarray, width: float, world: int, bounds=None) -> np.ndarray:
     """Owning rank of every x coordinate (x in [0, width))."""
-    bounds = np.array([slab_bound(width, r, world) for r in range(world + 1)], dtype=np.float32)
-    owner = np.searchsorted(bounds, np.asarray(x, dtype=np.float32), side="right") - 1
+    b = slab_bounds_array(width, world, bounds)
+    owner = np.searchsorted(b, np.asarray(x, dtype=np.float32), side="right") - 1
     return np.clip(owner, 0, world - 1).astype(np.int32)
 
 
-def partition(particles: np.ndarray, counts: np.ndarray, width: float, rank: int, world: int):
+def partition(particles: np.ndarray, counts: np.ndarray, width: float, rank: int, world: int, bounds=None):
     """(particles, counts, ids) owned by `rank`: the subset whose x lies in its slab, ids =
     original indices."""
-    owner = slab_owner(particles["pos"][:, 0], width, world)
+    owner = slab_owner(particles["pos"][:, 0], width, world, bounds)
     ids = np.nonzero(owner == rank)[0].astype(np.int32)
     return particles[ids], np.asarray(counts, np.int32)[ids], ids
+
+
+def balanced_bounds(hist: np.ndarray, width: float, world: int, min_width: float) -> np.ndarray:
+    """Slab bounds with (nearly) equal particle counts from a histogram of x over [0, width) — for clustered
+    states, where the uniform split would put almost everything on one or two ranks (the reference's own spawn
+    rule fills a centred 2000-wide cube, ParticleSimulation.cu:45-55).  Every slab stays at least `min_width`
+    (one interaction radius) wide; bounds sit on histogram bin edges, bounds[0] = 0, bounds[world] = width."""
+    hist = np.asarray(hist, dtype=np.float64)
+    nb = len(hist)
+    assert world * min_width <= width * (1 + 1e-6), "the box is too narrow for that many slabs of this radius"
+    edges = np.linspace(0.0, float(width), nb + 1)
+    cdf = np.concatenate([[0.0], np.cumsum(hist)])
+    total = cdf[-1]
+    b = np.zeros(world + 1, dtype=np.float64)
+    b[world] = float(width)
+    for r in range(1, world):
+        want = total * r / world
+        k = int(np.searchsorted(cdf, want, side="left"))
+        x = edges[min(max(k, 0), nb)]
+        x = max(x, b[r - 1] + min_width)                       # wide enough itself ...
+        x = min(x, float(width) - (world - r) * min_width)     # ... and room for the slabs to its right
+        b[r] = x
+    out = b.astype(np.float32)
+    out[0] = 0.0
+    out[world] = np.float32(width)
+    for r in range(world):  # float32 rounding must not eat the minimum width
+        if out[r + 1] - out[r] < np.float32(min_width):
+            out[r + 1] = np.nextafter(np.float32(out[r] + np.float32(min_width)), np.float32(np.inf))
+    out[world] = np.float32(width)
+    return out
+
+
+def interaction_radius(params, radio) -> float:
+    """R_max = radius * (1 + max(0, max_t radio_t * ratioWithLFO)) (ParticleSimulation.cu:108-110)."""
+    a = 1.0 + max(0.0, float(np.max(np.asarray(radio, np.float64) * float(params.ratioWithLFO))))
+    return float(params.radius) * a
 
 
 def broadcast_bytes(data: bytes | None, nbytes: int, src: int = 0) -> bytes:
@@ -160,8 +205,52 @@ def gather_particles(particles: np.ndarray, counts: np.ndarray, ids: np.ndarray,
     return out, cnt
 
 
-def make_slab_sim(params, raw, radio, n_total, seed, mode, capacity_factor=1.5, force_table=None):
-    """Creates this rank's simulation, joins the ring and spawns the global initial condition."""
+def all_reduce_array(a: np.ndarray) -> np.ndarray:
+    """Element-wise sum over the ranks of a float64 array."""
+    import torch
+    import torch.distributed as dist
+
+    if not dist.is_initialized():
+        return np.asarray(a, np.float64)
+    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+    t = torch.tensor(np.asarray(a, np.float64), dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t.cpu().numpy()
+
+
+def rebalance(sim, radio, bins: int = 4096, margin: float = 1.002):
+    """Moves the slab bounds to equal particle counts (all ranks call this together, between steps): global x
+    histogram -> balanced_bounds -> every particle goes to the rank that owns its x under the new bounds ->
+    cf_slab_set_bounds + upload.  Host-mediated (download, object all-gather, upload): a rare operation.
+    Returns (bounds, owned count of this rank)."""
+    import torch.distributed as dist
+
+    rank, world, _ = env_rank()
+    width = float(sim.params.canvasWidth)
+    pp, cc, ii = sim.downloadOwned()
+    hist, _ = np.histogram(pp["pos"][:, 0], bins=bins, range=(0.0, width))
+    hist = all_reduce_array(hist)
+    bounds = balanced_bounds(hist, width, world, interaction_radius(sim.params, radio) * margin)
+    owner = slab_owner(pp["pos"][:, 0], width, world, bounds)
+    if dist.is_initialized():
+        outgoing = [(pp[owner == r].tobytes(), cc[owner == r].tobytes(), ii[owner == r].tobytes()) for r in range(world)]
+        incoming = [None] * world
+        gathered = [None] * world
+        dist.all_gather_object(gathered, outgoing)
+        incoming = [g[rank] for g in gathered]
+        pp = np.concatenate([np.frombuffer(b[0], PARTICLE) for b in incoming])
+        cc = np.concatenate([np.frombuffer(b[1], np.int32) for b in incoming])
+        ii = np.concatenate([np.frombuffer(b[2], np.int32) for b in incoming])
+        order = np.argsort(ii, kind="stable")   # deterministic upload order
+        pp, cc, ii = pp[order], cc[order], ii[order]
+    sim.setSlabBounds(bounds)
+    sim.uploadOwned(pp, cc, ii)
+    return bounds, len(ii)
+
+
+def make_slab_sim(params, raw, radio, n_total, seed, mode, capacity_factor=1.5, force_table=None, bounds=None):
+    """Creates this rank's simulation, joins the ring and spawns the global initial condition.  `bounds`: slab
+    bounds for clustered states (balanced_bounds), the same array on every rank."""
     import torch
 
     from .sim import ParticleSimulation
@@ -181,6 +270,8 @@ def make_slab_sim(params, raw, radio, n_total, seed, mode, capacity_factor=1.5, 
     sim.setOption("global_particle_count", n_total)   # the cell grid derives from rank-invariant numbers only
     sim.commInit(rank, world, capacity)
     connect_ring(sim, rank, world)
+    if bounds is not None:
+        sim.setSlabBounds(bounds)
     if seed is not None:
         sim.initParticlesGlobal(n_total, seed, mode)
     return sim, rank, world

@@ -17,12 +17,16 @@ import oracle as O  # noqa: E402
 import util as U  # noqa: E402
 
 
-def run_case(name, p, table, radio, state, counts, steps, graph, rank, world):
+def run_case(name, p, table, radio, state, counts, steps, graph, rank, world, balanced=False):
     import torch.distributed as dist
     n = len(state)
     lp = U.to_lib_params(p)
-    sim, rank, world = cfd.make_slab_sim(lp, None, radio, n, None, cf.INIT_UNIFORM, force_table=table)
-    mine, mcounts, ids = cfd.partition(state, counts, p.canvasWidth, rank, world)
+    bounds = None
+    if balanced:  # clustered state: equal-count slabs from the x histogram, every slab >= one interaction radius
+        hist, _ = np.histogram(state["pos"][:, 0], bins=4096, range=(0.0, float(p.canvasWidth)))
+        bounds = cfd.balanced_bounds(hist, p.canvasWidth, world, cfd.interaction_radius(lp, radio) * 1.002)
+    sim, rank, world = cfd.make_slab_sim(lp, None, radio, n, None, cf.INIT_UNIFORM, force_table=table, bounds=bounds)
+    mine, mcounts, ids = cfd.partition(state, counts, p.canvasWidth, rank, world, bounds)
     sim.uploadOwned(mine, mcounts, ids)
     want_state, want_counts = state, counts
     first_ids = set(ids.tolist())
@@ -49,6 +53,9 @@ def run_case(name, p, table, radio, state, counts, steps, graph, rank, world):
                     es |= U.edge_set(np.frombuffer(b, cf.EDGE))
                 assert es == U.edge_set(O.graph(got, graph[0], graph[1], canvas=p.canvas, method="cells")), f"{name} step {step}: edges"
             want_state, want_counts = got, gcnt
+        if balanced and step == steps // 2:
+            # re-balance in the middle of the run: new bounds from the current x histogram, particles redistributed
+            _, owned_now = cfd.rebalance(sim, radio)
         # every rank continues from its own device state (no re-upload): real migration
     # migration is applied by the cell-list build that follows a step (the graph build / cellKeys above)
     pp, _, ii = sim.downloadOwned()
@@ -56,12 +63,17 @@ def run_case(name, p, table, radio, state, counts, steps, graph, rank, world):
     lo, hi = sim.slabBounds()
     assert np.all((pp["pos"][:, 0] >= lo) & (pp["pos"][:, 0] < hi)), f"{name}: a rank holds a particle outside its slab"
     st = sim.stats()
+    owned = [int.from_bytes(b, "little") for b in cfd.all_gather_bytes(int(st.n_owned).to_bytes(8, "little"))]
+    balance = max(owned) * world / max(sum(owned), 1)
+    if balanced:
+        assert balance <= 1.3, f"{name}: owned particles per rank {owned} (max/mean {balance:.2f})"
     # the cell grid must be the same on every rank (it once depended on the rank's own count)
     grids = cfd.all_gather_bytes(bytes(np.int32(list(st.grid)[1:]).tobytes()))
     assert len(set(grids)) == 1, f"{name}: ranks disagree on the (y, z) grid: {[np.frombuffer(g, np.int32).tolist() for g in grids]}"
     if rank == 0:
         print(f"DIST_CASE_OK {name} world={world} n={n} steps={steps} migrated={int(total_migrated)} "
-              f"ghosts_rank0={st.n_ghost} grid={list(st.grid)} force_kernel={st.force_kernel}", flush=True)
+              f"ghosts_rank0={st.n_ghost} grid={list(st.grid)} force_kernel={st.force_kernel} "
+              f"owned_max_over_mean={balance:.3f}", flush=True)
     sim.close()
     cfd.barrier()
     return int(total_migrated)
@@ -86,6 +98,17 @@ def main():
     state, counts = U.random_state(100_000, 6, 31, p.canvas, "uniform", vel_scale=300.0)
     #    (no graph here: the rule's 200 exceeds the one-cell ghost layer of this fine grid, which slab mode refuses)
     run_case("default-100k-sparse", p, table, radio, state, counts, 3, None, rank, world)
+    # D. the reference's own spawn rule (centred 2000-wide cube, ParticleSimulation.cu:45-55) and a blob state: the
+    #    uniform split would put everything on one or two ranks; equal-count slabs + a re-balance mid-run
+    p = O.Params()
+    raw, radio = O.default_tables(6)
+    table = O.force_table(raw, 6, p.forceRange, p.forceBias, p.forceOffset)
+    state = O.init_particles(100_000, 6, 0x5EED0002, cf.INIT_SPAWN_CUBE, p.canvas)
+    run_case("spawn-cube-100k", p, table, radio, state, np.zeros(len(state), np.int32), 4, None, rank, world, balanced=True)
+    p, table, radio = U.config("pulser", delta_t=0.9)
+    state, counts = U.random_state(80_000, 6, 37, p.canvas, "blobs", vel_scale=40.0)
+    if world * cfd.interaction_radius(U.to_lib_params(p), radio) * 1.002 <= p.canvasWidth:
+        run_case("blobs-80k", p, table, radio, state, counts, 4, (200.0, 5), rank, world, balanced=True)
     if rank == 0:
         assert mig > 0, "test did not exercise migration"
         print(f"DIST_CHECK_OK world={world} migrated={mig}", flush=True)

@@ -9,6 +9,7 @@ import sys
 import textwrap
 
 import numpy as np
+import pytest
 
 import util as U
 from cellflow_b200 import dist as cfd
@@ -89,3 +90,27 @@ def test_gloo_world_size_2(tmp_path):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     assert "GLOO_OK" in r.stdout
+
+
+def test_balanced_bounds_equalise_a_clustered_state():
+    """Slab bounds from the x histogram (cellflow_b200/dist.py): the reference's spawn cube (2000 wide in an 8000 box)
+    split over 8 ranks — equal counts, every slab at least one interaction radius wide, ends pinned to the box."""
+    from cellflow_b200 import dist as cfd
+    rng = np.random.default_rng(3)
+    x = (rng.random(200_000) * 2000 + 3000).astype(np.float32)
+    hist, _ = np.histogram(x, bins=4096, range=(0.0, 8000.0))
+    b = cfd.balanced_bounds(hist, 8000.0, 8, 42.2)
+    assert b[0] == 0 and b[-1] == 8000 and np.all(np.diff(b) >= 42.2)
+    owned = np.bincount(cfd.slab_owner(x, 8000.0, 8, b), minlength=8)
+    assert owned.max() * 8 / owned.sum() <= 1.02
+    # a radius that does not leave room for equal counts: the widths win, nothing overlaps, all particles are owned
+    b = cfd.balanced_bounds(hist, 8000.0, 8, 600.0)
+    assert np.all(np.diff(b) >= 600.0) and b[-1] == 8000
+    assert np.bincount(cfd.slab_owner(x, 8000.0, 8, b), minlength=8).sum() == len(x)
+    # uniform state: the uniform split comes back (to bin resolution)
+    xu = (rng.random(400_000) * 8000).astype(np.float32)
+    hu, _ = np.histogram(xu, bins=4096, range=(0.0, 8000.0))
+    bu = cfd.balanced_bounds(hu, 8000.0, 4, 300.0)
+    assert np.allclose(bu, [0, 2000, 4000, 6000, 8000], atol=30)
+    with pytest.raises(AssertionError):
+        cfd.balanced_bounds(hist, 8000.0, 8, 1200.0)

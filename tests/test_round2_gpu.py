@@ -202,6 +202,7 @@ def test_block_counters_of_the_tile_kernel():
     assert np.array_equal(pc, ic) and plain.tobytes() == inst.tobytes()
     acc = int(ic.sum())
     assert st.force_kernel == 3
-    assert st.evaluated_pair_lanes >= acc + len(state) - 128 * 0 and st.exact_tested_pairs >= st.evaluated_pair_lanes
-    assert st.exact_tested_pairs <= st.tested_pairs * 1.3 + 1e6      # never more than the stencil (plus chunk padding)
+    # every accepted pair (and every particle's own slot) sits in an evaluated block; every evaluated block was tested.
+    # (Blocks count 128 pair-lanes each, padded lanes included, so they may exceed the stencil's pair count.)
+    assert st.evaluated_pair_lanes >= acc + len(state) and st.exact_tested_pairs >= st.evaluated_pair_lanes
     sim.close()
