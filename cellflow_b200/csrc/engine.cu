@@ -122,6 +122,7 @@ struct cf_sim {
     size_t gstart_cap = 0;
     unsigned long long* d_graph_occ = nullptr; // sum over (type, cell) keys of occupancy^2, last build
     unsigned long long h_graph_occ = 0;
+    unsigned long long* h_graph_occ_pin = nullptr; // pinned mirror every build refreshes without synchronising
     double graph_mean_occ = 0.0;               // mean same-key companions per particle, last build
     int opt_graph_kernel = 0;                  // 0 auto, 1 thread per particle, 2 warp per particle
     int last_graph_kernel = 0;
@@ -145,6 +146,7 @@ struct cf_sim {
     uint32_t* hv[2] = {nullptr, nullptr};
     int* h_cell_of = nullptr;
     float4* h_pos = nullptr;
+    float* h_xyz[3] = {nullptr, nullptr, nullptr}; // the same copy as SoA planes (bulk-copy staging)
     uint32_t* h_comp = nullptr;
     size_t homog_cap = 0;
     int* h_start = nullptr;
@@ -190,6 +192,7 @@ struct cf_sim {
     // options
     int opt_force_kernel = 0; // 0 auto, 1 per-particle, 2 tile (generation 3), 3 tile (generation 4)
     int opt_timing = 0;
+    int opt_t4_stage = 0;     // 1: j chunks staged with cp.async.bulk + mbarrier from SoA planes (per-type radii only)
     int opt_count_blocks = 0; // instrumented tile kernel: counts exact-tested / evaluated blocks (cf_stats)
     unsigned long long* d_block_counts = nullptr;
     bool block_counts_valid = false;
@@ -656,6 +659,8 @@ extern "C" int cf_create(int particle_count, int num_types, int device, cf_sim**
     if (rc == 0 && cudaMemset(s->d_cell_occ, 0, 2 * sizeof(unsigned long long)) != cudaSuccess) rc = fail(CF_ERR_CUDA, "cudaMemset");
     if (rc == 0 && cudaMallocHost(&s->h_cell_occ, sizeof(unsigned long long)) != cudaSuccess) rc = fail(CF_ERR_CUDA, "cudaMallocHost");
     if (rc == 0) *s->h_cell_occ = 0;
+    if (rc == 0 && cudaMallocHost(&s->h_graph_occ_pin, sizeof(unsigned long long)) != cudaSuccess) rc = fail(CF_ERR_CUDA, "cudaMallocHost");
+    if (rc == 0) *s->h_graph_occ_pin = 0;
     if (rc == 0 && cudaMalloc(&s->d_half, CF_T_MAX * sizeof(float)) != cudaSuccess) rc = fail(CF_ERR_CUDA, "cudaMalloc");
     if (rc == 0) {
         cudaDeviceProp prop;
@@ -699,6 +704,7 @@ extern "C" int cf_destroy(cf_sim* s) {
     cudaFree(s->d_tile_ctrl);
     cudaFree(s->d_cell_occ);
     if (s->h_cell_occ) cudaFreeHost(s->h_cell_occ);
+    if (s->h_graph_occ_pin) cudaFreeHost(s->h_graph_occ_pin);
     cudaFree(s->d_half);
     for (int b = 0; b < 2; b++) {
         cudaFree(s->hk[b]);
@@ -706,6 +712,7 @@ extern "C" int cf_destroy(cf_sim* s) {
     }
     cudaFree(s->h_cell_of);
     cudaFree(s->h_pos);
+    for (int a = 0; a < 3; a++) cudaFree(s->h_xyz[a]);
     cudaFree(s->h_comp);
     cudaFree(s->h_start);
     for (auto& ev : s->ev_pool)
@@ -1039,6 +1046,7 @@ static int build_homog_copy(cf_sim* s) {
         cudaFree(s->h_pos);
         cudaFree(s->h_comp);
         s->h_cell_of = nullptr, s->h_pos = nullptr, s->h_comp = nullptr;
+        for (int a = 0; a < 3; a++) cudaFree(s->h_xyz[a]), s->h_xyz[a] = nullptr;
         s->homog_cap = (size_t)nslots + (size_t)nslots / 8 + 1024;
         for (int b = 0; b < 2; b++) {
             CU(cudaMalloc(&s->hk[b], s->homog_cap * sizeof(uint32_t)));
@@ -1046,6 +1054,10 @@ static int build_homog_copy(cf_sim* s) {
         }
         CU(cudaMalloc(&s->h_cell_of, s->homog_cap * sizeof(int)));
         CU(cudaMalloc(&s->h_pos, s->homog_cap * sizeof(float4)));
+        for (int a = 0; a < 3; a++) { // + one chunk of slack: a bulk copy always moves 128 elements
+            CU(cudaMalloc(&s->h_xyz[a], (s->homog_cap + 256) * sizeof(float)));
+            CU(cudaMemsetAsync(s->h_xyz[a], 0, (s->homog_cap + 256) * sizeof(float), s->stream));
+        }
         CU(cudaMalloc(&s->h_comp, s->homog_cap * sizeof(uint32_t)));
     }
     if ((size_t)nkeys + 2 > s->h_start_cap) {
@@ -1061,7 +1073,7 @@ static int build_homog_copy(cf_sim* s) {
     int src = 0;
     if (int rc = radix_sort_pairs(s, s->hk, s->hv, nslots, (long long)nrow * s->T + 1, &src, d_nslots)) return rc;
     LAUNCH(s, homog_gather_kernel, div_up(nslots, 256), 256, 0, s->hk[src], s->hv[src], pos, s->h_cell_of, nz, nslots,
-           d_nslots, s->h_pos, s->h_comp);
+           d_nslots, s->h_pos, s->h_comp, s->opt_t4_stage ? s->h_xyz[0] : nullptr, s->h_xyz[1], s->h_xyz[2]);
     LAUNCH(s, homog_bounds_kernel, div_up(nkeys + 1, 256), 256, 0, s->h_comp, nslots, d_nslots, s->h_start, nkeys);
     return 0;
 }
@@ -1141,7 +1153,10 @@ static int launch_force(cf_sim* s) {
                 s->block_counts_valid = true;
                 return 0;
             }
-            if (homog)
+            if (homog && s->opt_t4_stage)
+                LAUNCH(s, (force_tile4_kernel<1, false, 1>), grid, T4_WARPS * 32, pad, pos, s->cell_start, s->h_pos, s->h_start,
+                       s->d_tiles, s->d_tile_ctrl, s->frc, s->sc, s->d_tables, nullptr, s->h_xyz[0], s->h_xyz[1], s->h_xyz[2]);
+            else if (homog)
                 LAUNCH(s, (force_tile4_kernel<1, false>), grid, T4_WARPS * 32, pad, pos, s->cell_start, s->h_pos, s->h_start,
                        s->d_tiles, s->d_tile_ctrl, s->frc, s->sc, s->d_tables, nullptr);
             else
@@ -1198,10 +1213,10 @@ static std::vector<char> step_signature(const cf_sim* s) {
     const void* ptrs[] = {s->pos[0], s->pos[1], s->vel[0], s->vel[1], s->id[0], s->id[1], s->frc, s->keys[0],
                           s->keys[1], s->vals[0], s->vals[1], s->hist, s->cell_start, s->d_tiles, s->d_tile_ctrl,
                           s->d_tables, s->d_half, s->hk[0], s->hk[1], s->hv[0], s->hv[1], s->h_cell_of, s->h_pos,
-                          s->h_comp, s->h_start};
+                          s->h_comp, s->h_start, s->h_xyz[0], s->h_xyz[1], s->h_xyz[2]};
     put(ptrs, sizeof(ptrs));
     int ints[] = {s->n, s->ncell, s->cur, s->opt_force_kernel, s->sorted_valid ? 1 : 0, s->half_bound_ok ? 1 : 0,
-                  s->planned_force_kernel, s->opt_t4_ctas, s->opt_count_blocks};
+                  s->planned_force_kernel, s->opt_t4_ctas, s->opt_count_blocks, s->opt_t4_stage};
     put(ints, sizeof(ints));
     return sig;
 }
@@ -1423,7 +1438,12 @@ static int graph_make_plan(cf_sim* s, float dist, int mc, GraphPlan& P) {
     // extra synchronisation): ~27 * mean occupancy candidates per particle; above ~250 the
     // warp-per-particle kernel wins (spawn cube, clustered states), below it thread-per-particle
     P.gkernel = s->opt_graph_kernel;
-    if (P.gkernel == 0) P.gkernel = 27.0 * s->graph_mean_occ >= 250.0 ? 2 : 1;
+    // (asynchronous builds never read the count back: the pinned mirror of an earlier build's occupancy stands in;
+    //  both kernels produce the same edge set, so the choice may depend on timing)
+    double occ = s->graph_mean_occ;
+    if (s->h_graph_occ_pin && s->graph_plan_count > 0 && s->n > 0)
+        occ = std::max(occ, (double)*s->h_graph_occ_pin / (double)s->graph_plan_count);
+    if (P.gkernel == 0) P.gkernel = 27.0 * occ >= 250.0 ? 2 : 1;
     return 0;
 }
 
@@ -1588,6 +1608,7 @@ extern "C" int cf_build_graph(cf_sim* s, float dist, int max_conn, int* n_edges)
     }
     s->last_graph_kernel = P.gkernel;
     if (gev) CU(cudaEventRecord(gev[1], s->stream));
+    CU(cudaMemcpyAsync(s->h_graph_occ_pin, s->d_graph_occ, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->stream));
     s->graph_gen = s->state_gen;
     s->graph_count_pending = true;
     s->graph_plan_count = s->slab ? std::max(s->n, 1) : P.count;
@@ -1800,6 +1821,7 @@ extern "C" int cf_set_option(cf_sim* s, const char* name, double value) {
     else if (k == "graph_kernel") s->opt_graph_kernel = (int)value; // 0 auto, 1 thread per particle, 2 warp per particle
     else if (k == "timing") s->opt_timing = (int)value;
     else if (k == "t4_ctas_per_sm") s->opt_t4_ctas = (int)value;
+    else if (k == "t4_stage") s->opt_t4_stage = (int)value;
     else if (k == "count_blocks") s->opt_count_blocks = (int)value, s->block_counts_valid = false;
     else if (k == "max_cells_per_particle") s->opt_max_cells_per_particle = value;
     else if (k == "cuda_graphs") s->opt_graphs = (int)value;

@@ -51,7 +51,34 @@ struct T4Shared {
     int2 sub[T4_WARPS][MODE ? T4_MAXSUB : TK_MAX_RUNS]; // [j0, j1) of every (sub-)run
     float4 cst[MODE ? T4_WARPS : 1][4][32];          // MODE 1: (c2, A, B, cut2) of (layer, lane) for the current sub-run
     float4 box[T4_WARPS][4][2];                      // (lo.xyz, prefilter threshold), (hi.xyz, -) of every layer
+    unsigned long long bar[T4_WARPS][2];             // STAGE 1: one mbarrier per (warp, stage buffer)
 };
+
+// ---- bulk-copy staging (STAGE 1): cp.async.bulk global -> shared, completion on an mbarrier (SASS: UBLKCP) ----
+__device__ __forceinline__ void t4_mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void t4_mbar_expect(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void t4_bulk_load(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ bool t4_mbar_try(unsigned bar, unsigned parity) {
+    unsigned ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
 
 __device__ __forceinline__ int t4_setlt(float a, float b) { // 0xffffffff if a < b else 0
     int r;
@@ -200,12 +227,20 @@ __device__ __forceinline__ void t4_chunk(unsigned sbase, const unsigned (&live)[
     }
 }
 
-template <int MODE, bool COUNT = false>
+// STAGE 0: the j chunk goes global -> registers (4 x LDG.128 per lane) -> shared (3-4 x STS.128, transposed to
+//          SoA), next chunk hinted into L1.
+// STAGE 1 (MODE 1 only): the type-sorted copy also exists as SoA planes (jx, jy, jz); one elected lane brings the
+//          next 128-j chunk in with three 512-byte cp.async.bulk copies that complete on the warp's mbarrier
+//          (UBLKCP), no register round trip, no transpose; chunk starts are aligned down to 4 elements (16 bytes)
+//          and the elements in front of the sub-run are masked.  A/B in profiles/r02_staging_ab.md.
+template <int MODE, bool COUNT = false, int STAGE = 0>
 __global__ void __launch_bounds__(T4_WARPS * 32, T4_MINB)
 force_tile4_kernel(const float4* __restrict__ pos4, const int* __restrict__ cell_start,
                    const float4* __restrict__ posj, const int* __restrict__ startj,
                    const int2* __restrict__ tiles, int* __restrict__ ctrl, float4* __restrict__ frc4, StepConst c,
-                   const DeviceTables* __restrict__ tables, unsigned long long* __restrict__ block_counts = nullptr) {
+                   const DeviceTables* __restrict__ tables, unsigned long long* __restrict__ block_counts = nullptr,
+                   const float* __restrict__ jx = nullptr, const float* __restrict__ jy = nullptr,
+                   const float* __restrict__ jz = nullptr) {
     __shared__ __align__(16) T4Shared<MODE> sm;
     // MODE 0: s_tab[tj*T + ti] = fv.  MODE 1: s_tab4[tj*T + ti] = (c2, fv*rep, -fv*att/Reff, cut2)
     __shared__ __align__(16) float s_tab[CF_TT_MAX * (MODE ? 4 : 1)];
@@ -222,6 +257,16 @@ force_tile4_kernel(const float4* __restrict__ pos4, const int* __restrict__ cell
             e[1] = fv * c.repulsion;
             e[2] = -(fv * (c.attraction * inv));
             e[3] = tables->cut2[i];
+        }
+    }
+    unsigned bar_addr = 0, bar_phase = 0; // STAGE 1: this warp's two mbarriers (+ 8 * buffer), their parity bits
+    if (STAGE) {
+        bar_addr = (unsigned)__cvta_generic_to_shared(&sm.bar[warp][0]);
+        if (lane == 0) {
+            t4_mbar_init(bar_addr, 1);
+            t4_mbar_init(bar_addr + 8, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         }
     }
     __syncthreads(); // the only block-level barrier: tables are read-only afterwards
@@ -345,7 +390,7 @@ force_tile4_kernel(const float4* __restrict__ pos4, const int* __restrict__ cell
 
         // ---- stream the chunks of all (sub-)runs; the next chunk is prefetched across run boundaries
         //      into L1 by a prefetch hint, which holds no registers ----
-        int si = -1, off = 0, end = 0; // cursor
+        int si = -1, off = 0, end = 0, lo = 0; // cursor: chunk [off, off + 128) of sub-run si = [lo, end)
         bool have;
 #define T4_ADVANCE()                                \
     do {                                            \
@@ -354,19 +399,53 @@ force_tile4_kernel(const float4* __restrict__ pos4, const int* __restrict__ cell
         while (off >= end) {                        \
             if (++si >= nsub) { have = false; break; } \
             const int2 e_ = wsub[si];               \
-            off = e_.x, end = e_.y;                 \
+            lo = e_.x, end = e_.y;                  \
+            off = STAGE ? (lo & ~3) : lo; /* bulk copies start on 16-byte boundaries */ \
         }                                           \
     } while (0)
         T4_ADVANCE();
         int cur_si = -1, buf = 0;
+        if (STAGE && have && lane == 0) { // first chunk of the tile: three plane copies onto buffer 0's barrier
+            t4_mbar_expect(bar_addr, 3 * T4_JC * 4);
+            t4_bulk_load(stage_addr, jx + off, T4_JC * 4, bar_addr);
+            t4_bulk_load(stage_addr + STRIDE, jy + off, T4_JC * 4, bar_addr);
+            t4_bulk_load(stage_addr + 2 * STRIDE, jz + off, T4_JC * 4, bar_addr);
+        }
         float sx = 0.f, sy = 0.f, sz = 0.f;
         bool wrap = false;
         while (have) {
-            const int csi = si, coff = off, cend = end;
+            const int csi = si, coff = off, cend = end, clo = lo;
             // ---- load and publish the chunk: lane l holds the quad j = coff + 4l .. 4l+3 ----
             const unsigned sbase = stage_addr + (unsigned)buf * (T4_JC * 4);
             float lox = T4_INF, loy = T4_INF, loz = T4_INF, hix = -T4_INF, hiy = -T4_INF, hiz = -T4_INF;
-            {
+            if (STAGE) {
+                // the chunk was requested one iteration ago: wait for its bytes, then every lane reads its own quad
+                while (!t4_mbar_try(bar_addr + 8u * (unsigned)buf, (bar_phase >> buf) & 1u)) {}
+                bar_phase ^= 1u << buf;
+                const unsigned a = sbase + 16u * (unsigned)lane;
+                float4 X, Y, Z;
+                asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(X.x), "=f"(X.y), "=f"(X.z), "=f"(X.w) : "r"(a));
+                asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(Y.x), "=f"(Y.y), "=f"(Y.z), "=f"(Y.w) : "r"(a + STRIDE));
+                asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(Z.x), "=f"(Z.y), "=f"(Z.z), "=f"(Z.w) : "r"(a + 2 * STRIDE));
+                const int j0 = coff + 4 * lane;
+                const bool v0 = j0 >= clo && j0 < cend, v1 = j0 + 1 >= clo && j0 + 1 < cend;
+                const bool v2 = j0 + 2 >= clo && j0 + 2 < cend, v3 = j0 + 3 >= clo && j0 + 3 < cend;
+                if (!(v0 && v1 && v2 && v3)) { // elements of another sub-run (or past the end): never in range
+                    if (!v0) X.x = Y.x = Z.x = TK_FAR;
+                    if (!v1) X.y = Y.y = Z.y = TK_FAR;
+                    if (!v2) X.z = Y.z = Z.z = TK_FAR;
+                    if (!v3) X.w = Y.w = Z.w = TK_FAR;
+                    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a), "f"(X.x), "f"(X.y), "f"(X.z), "f"(X.w) : "memory");
+                    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a + STRIDE), "f"(Y.x), "f"(Y.y), "f"(Y.z), "f"(Y.w) : "memory");
+                    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a + 2 * STRIDE), "f"(Z.x), "f"(Z.y), "f"(Z.z), "f"(Z.w) : "memory");
+                }
+                lox = fminf(fminf(v0 ? X.x : T4_INF, v1 ? X.y : T4_INF), fminf(v2 ? X.z : T4_INF, v3 ? X.w : T4_INF));
+                hix = fmaxf(fmaxf(v0 ? X.x : -T4_INF, v1 ? X.y : -T4_INF), fmaxf(v2 ? X.z : -T4_INF, v3 ? X.w : -T4_INF));
+                loy = fminf(fminf(v0 ? Y.x : T4_INF, v1 ? Y.y : T4_INF), fminf(v2 ? Y.z : T4_INF, v3 ? Y.w : T4_INF));
+                hiy = fmaxf(fmaxf(v0 ? Y.x : -T4_INF, v1 ? Y.y : -T4_INF), fmaxf(v2 ? Y.z : -T4_INF, v3 ? Y.w : -T4_INF));
+                loz = fminf(fminf(v0 ? Z.x : T4_INF, v1 ? Z.y : T4_INF), fminf(v2 ? Z.z : T4_INF, v3 ? Z.w : T4_INF));
+                hiz = fmaxf(fmaxf(v0 ? Z.x : -T4_INF, v1 ? Z.y : -T4_INF), fmaxf(v2 ? Z.z : -T4_INF, v3 ? Z.w : -T4_INF));
+            } else {
                 float4 q[4];
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
@@ -392,9 +471,21 @@ force_tile4_kernel(const float4* __restrict__ pos4, const int* __restrict__ cell
                 }
             }
             __syncwarp();
-            // the next chunk (possibly of the next run): prefetch hint, 128 float4 = 2 KiB <= 17 lines
             T4_ADVANCE();
-            if (have && lane < 17) {
+            if (STAGE) {
+                // the next chunk (possibly of the next sub-run) -> the other buffer, which this warp finished
+                // reading one chunk ago (the __syncwarp above orders those reads before the request)
+                if (have && lane == 0) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // generic accesses of that buffer first
+                    const unsigned nb = bar_addr + 8u * (unsigned)(buf ^ 1);
+                    const unsigned dst = stage_addr + (unsigned)(buf ^ 1) * (T4_JC * 4);
+                    t4_mbar_expect(nb, 3 * T4_JC * 4);
+                    t4_bulk_load(dst, jx + off, T4_JC * 4, nb);
+                    t4_bulk_load(dst + STRIDE, jy + off, T4_JC * 4, nb);
+                    t4_bulk_load(dst + 2 * STRIDE, jz + off, T4_JC * 4, nb);
+                }
+            } else if (have && lane < 17) {
+                // the next chunk (possibly of the next run): prefetch hint, 128 float4 = 2 KiB <= 17 lines
                 const float4* pf = posj + min(off + 8 * lane, end - 1);
                 asm volatile("prefetch.global.L1 [%0];" ::"l"(pf));
             }
@@ -496,13 +587,16 @@ __global__ void homog_key_kernel(const float4* __restrict__ pos4, const int* __r
 __global__ void homog_gather_kernel(const uint32_t* __restrict__ skeys, const uint32_t* __restrict__ svals,
                                     const float4* __restrict__ pos4, const int* __restrict__ cell_of, int nz,
                                     int nslots_upper, const int* __restrict__ d_nslots, float4* __restrict__ posj,
-                                    uint32_t* __restrict__ comp) {
+                                    uint32_t* __restrict__ comp, float* __restrict__ jx, float* __restrict__ jy,
+                                    float* __restrict__ jz) {
     const int nslots = d_nslots ? min(*d_nslots, nslots_upper) : nslots_upper;
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= nslots) return;
     const uint32_t src = svals[k];
     const int cell = cell_of[src];
-    posj[k] = pos4[src];
+    const float4 p = pos4[src];
+    posj[k] = p;
+    if (jx) jx[k] = p.x, jy[k] = p.y, jz[k] = p.z; // SoA planes for the bulk-copy staging (STAGE 1)
     comp[k] = cell >= 0 ? skeys[k] * (uint32_t)nz + (uint32_t)(cell % nz) : 0xffffffffu;
 }
 

@@ -206,3 +206,25 @@ def test_block_counters_of_the_tile_kernel():
     # (Blocks count 128 pair-lanes each, padded lanes included, so they may exceed the stencil's pair count.)
     assert st.evaluated_pair_lanes >= acc + len(state) and st.exact_tested_pairs >= st.evaluated_pair_lanes
     sim.close()
+
+
+def test_bulk_copy_staging_is_bit_identical():
+    """Option "t4_stage" = 1: the j chunks of the type-sorted copy arrive through cp.async.bulk + mbarrier from SoA
+    planes (chunk starts aligned down to 16 bytes, foreign elements masked) instead of LDG -> registers -> STS.
+    Same pairs in the same order: counts and forces are bit-identical to the default staging, and match the oracle."""
+    sim, p, table, radio, state, counts = small_sim(n=60000, kernel=3)
+    sim.simulate(steps=2)
+    a, ac = sim.getParticleData(), sim.getNeighborCounts()
+    sim.setParticleData(state, counts)
+    sim.setOption("t4_stage", 1)
+    sim.simulate(steps=2)
+    b, bc = sim.getParticleData(), sim.getNeighborCounts()
+    assert sim.stats().force_kernel == 3
+    assert np.array_equal(ac, bc) and a.tobytes() == b.tobytes()
+    sim.setParticleData(state, counts)
+    sim.simulate()
+    got, gcnt = sim.getParticleData(), sim.getNeighborCounts()
+    want, wcnt, fabs = O.step(state, counts, p, table, radio, "cells", THREADS)
+    assert np.array_equal(gcnt, wcnt)
+    assert U.force_rel_err(got["acc"], want["acc"], fabs, U.force_multiplier_of(p, wcnt, counts)).max() <= U.FORCE_RTOL
+    sim.close()
