@@ -388,7 +388,7 @@ def run_ours(args):
     hbm = float(peaks.get("hbm_gbs", 6650.0))
     # cell-list build: key + 2-3 radix passes + reorder + bounds, algorithmic bytes per particle
     key_bits = max(1, int(np.ceil(np.log2(max(2, int(np.prod(r["grid"])) * 64)))))
-    passes = -(-key_bits // 9)
+    passes = -(-key_bits // 10)
     sort_bytes = 24 + passes * 20 + 76
     roofline = {
         "kernel": "pair_force", "bound": "fp32", "achieved": round(achieved, 3), "peak": round(tf.value, 2),

@@ -1,7 +1,7 @@
 // kernels_sort.cuh — stable LSD radix sort of (key, slot) pairs: the cell-list build (HBM-bound).
 //
 // Keys are small (cell * 64 + Hilbert sub-cell < 2^18 at the bench default, type * ncell + cell for the
-// proximity graph), so only ceil(log2(range)) bits are sorted, in passes of up to RS_MAX_BITS = 9 bits
+// proximity graph), so only ceil(log2(range)) bits are sorted, in passes of up to RS_MAX_BITS = 10 bits
 // (two passes for <= 2^18 keys).  Each pass is
 //     per-block digit histogram -> one scan block PER DIGIT (parallel) -> stable scatter,
 // and the sort is stable and therefore deterministic: the slot order inside a cell (hence the force
@@ -23,7 +23,7 @@
 
 #define RS_THREADS 256
 #define RS_WARPS (RS_THREADS / 32)
-#define RS_MAX_BITS 9
+#define RS_MAX_BITS 10 // 1024 bins: the 18-bit cell key and the <= 20-bit (type, cell) key of the graph are two passes
 #define RS_MAX_BINS (1 << RS_MAX_BITS)
 
 // Key sources of the histogram kernel -----------------------------------------------------------
@@ -135,15 +135,21 @@ rs_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restri
     const int nbins = (int)mask + 1;
     const int block_base = blockIdx.x * (RS_THREADS * R * groups);
     if (block_base >= n) return;
-    // ---- digit bases: exclusive scan of the digit totals (<= 512, two per thread) ----
+    // ---- digit bases: exclusive scan of the digit totals (RS_MAX_BINS / RS_THREADS consecutive digits per thread) ----
     {
-        const int d0 = 2 * tid, d1 = 2 * tid + 1;
-        const uint32_t t0 = d0 < nbins ? totals[d0] : 0u, t1 = d1 < nbins ? totals[d1] : 0u;
-        uint32_t incl = t0 + t1;
+        constexpr int DPT = RS_MAX_BINS / RS_THREADS;
+        uint32_t t[DPT], sum = 0;
+#pragma unroll
+        for (int u = 0; u < DPT; u++) {
+            const int d = DPT * tid + u;
+            t[u] = d < nbins ? totals[d] : 0u;
+            sum += t[u];
+        }
+        uint32_t incl = sum;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += t;
+            const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
         }
         if (lane == 31) wsum[warp] = incl;
         __syncthreads();
@@ -151,9 +157,13 @@ rs_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restri
 #pragma unroll
         for (int w = 0; w < RS_WARPS; w++)
             if (w < warp) wbase += wsum[w];
-        const uint32_t excl = wbase + incl - (t0 + t1);
-        if (d0 < nbins) running[d0] = excl + hist[d0 * nblocks + blockIdx.x];
-        if (d1 < nbins) running[d1] = excl + t0 + hist[d1 * nblocks + blockIdx.x];
+        uint32_t run = wbase + incl - sum;
+#pragma unroll
+        for (int u = 0; u < DPT; u++) {
+            const int d = DPT * tid + u;
+            if (d < nbins) running[d] = run + hist[d * nblocks + blockIdx.x];
+            run += t[u];
+        }
     }
     const uint32_t lt = (1u << lane) - 1u;
     for (int g = 0; g < groups; g++) {

@@ -34,7 +34,12 @@
 #pragma once
 #include "kernels_tile.cuh"
 
+#ifndef T4_WARPS
 #define T4_WARPS 4
+#endif
+#ifndef T4_PAIRSKIP
+#define T4_PAIRSKIP 0
+#endif
 #ifndef T4_MINB
 #define T4_MINB 5 // resident CTAs per SM the register budget is set for (96 registers per thread)
 #endif
@@ -198,6 +203,10 @@ __device__ __forceinline__ void t4_chunk(unsigned sbase, const unsigned (&live)[
             // every layer of a live quad: there the extra branch costs more than the tests it saves
             // (measured: eater 4.89 -> 4.76 ms without it, pulser 1.96 -> 2.30 ms without it)
             if (MODE == 0 && !(live[k] & bit)) continue;
+#if T4_PAIRSKIP
+            // MODE 1: one warp-uniform branch per PAIR of layers (half the branches of the per-layer form)
+            if (MODE == 1 && !((live[k & ~1] | live[k | 1]) & bit)) continue;
+#endif
             float4 cs = make_float4(c2u, pau, pbu, cutu);
             if (MODE == 1) // (c2, A, B, cut2) of (layer k, this lane): 32-bit shared address, no generic pointer
                 asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(cs.x), "=f"(cs.y), "=f"(cs.z), "=f"(cs.w) : "r"(cst_addr + 512u * k));
