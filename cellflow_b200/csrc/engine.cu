@@ -1130,9 +1130,9 @@ static int launch_force(cf_sim* s) {
         if (homog)
             if (int rc = build_homog_copy(s)) return rc;
         CU(cudaMemsetAsync(s->d_tile_ctrl, 0, 2 * sizeof(int), s->stream));
-        LAUNCH(s, build_tiles_kernel, div_up(s->ncell, 256), 256, 0, s->cell_start, s->ncell, s->sc.x_off,
-               s->sc.x_off + s->sc.x_cells - 1,
-               s->sc.dims[1] * s->sc.dims[2], s->d_tiles, s->d_tile_ctrl);
+        for (int part = 0; part < 2; part++) // full tiles first, partly filled ones last
+            LAUNCH(s, build_tiles_kernel, div_up(s->ncell, 256), 256, 0, s->cell_start, s->ncell, s->sc.x_off,
+                   s->sc.x_off + s->sc.x_cells - 1, s->sc.dims[1] * s->sc.dims[2], s->d_tiles, s->d_tile_ctrl, part);
         if (kernel == 3) { // persistent grid: 5 CTAs of 4 independent warps per SM (96 registers per thread)
             // experiment knob (cf_set_option "t4_ctas_per_sm"): fewer resident CTAs, enforced with dynamic shared memory
             const int ctas = s->opt_t4_ctas > 0 ? std::min(s->opt_t4_ctas, T4_MINB) : T4_MINB;

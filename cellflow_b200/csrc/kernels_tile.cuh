@@ -96,20 +96,30 @@ __global__ void count_tests_kernel(const int* __restrict__ cell_start, int ncell
     if ((threadIdx.x & 31) == 0 && local) atomicAdd(out, local);
 }
 
-// Tile list: one thread per cell appends ceil(n_cell / TK_TI) tiles.  Tile order is arbitrary
-// (results do not depend on it); ctrl[0] = number of tiles, ctrl[1] = fetch counter.
+// Tile list: one thread per cell appends ceil(n_cell / TK_TI) tiles; ctrl[0] = number of tiles, ctrl[1] = fetch
+// counter.  Two passes (part 0: the full 128-particle tiles, part 1: the partly filled last tile of every cell),
+// so the persistent grid works through the expensive tiles first and finishes on the cheap ones — longest-
+// processing-time-first; with one arbitrary order the warps that drew a full tile last left the others idle for
+// up to a tile's duration (~1.5 ms at the bench default: 10 % of the SM-cycles, profiles/r02_*).  Results do not
+// depend on the order.
 __global__ void build_tiles_kernel(const int* __restrict__ cell_start, int ncell, int first_cell_x,
                                    int last_cell_x, int cells_per_x, int2* __restrict__ tiles,
-                                   int* __restrict__ ctrl) {
+                                   int* __restrict__ ctrl, int part) {
     int cell = blockIdx.x * blockDim.x + threadIdx.x;
     if (cell >= ncell) return;
     int cx = cell / cells_per_x;
     if (cx < first_cell_x || cx > last_cell_x) return; // ghost layers are never i-cells
     int n = cell_start[cell + 1] - cell_start[cell];
     if (n <= 0) return;
-    int nt = (n + TK_TI - 1) / TK_TI;
-    int base = atomicAdd(&ctrl[0], nt);
-    for (int k = 0; k < nt; k++) tiles[base + k] = make_int2(cell, k);
+    const int nfull = n / TK_TI;
+    if (part == 0) {
+        if (nfull == 0) return;
+        int base = atomicAdd(&ctrl[0], nfull);
+        for (int k = 0; k < nfull; k++) tiles[base + k] = make_int2(cell, k);
+    } else if (n > nfull * TK_TI) {
+        int base = atomicAdd(&ctrl[0], 1);
+        tiles[base] = make_int2(cell, nfull);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
