@@ -1118,7 +1118,10 @@ static int launch_force(cf_sim* s) {
            s->d_cell_occ, s->h_cell_occ);
     s->last_force_kernel = kernel;
     if (kernel == 2 || kernel == 3) {
-        size_t need = (size_t)s->ncell + (size_t)(s->slab ? s->cap_own : n) / TK_TI + 2;
+        const bool homog = kernel == 3 && !s->sc.uniform_radius;
+        // particles per tile: 128 (generation 3), 32 x layers of the generation-4 instantiation in use
+        const int tile_i = kernel == 3 ? 32 * t4_ipt(homog ? 1 : 0) : TK_TI;
+        size_t need = (size_t)s->ncell + (size_t)(s->slab ? s->cap_own : n) / tile_i + 2;
         if (need > s->tiles_cap) {
             CU(cudaStreamSynchronize(s->stream));
             cudaFree(s->d_tiles);
@@ -1126,18 +1129,19 @@ static int launch_force(cf_sim* s) {
             s->tiles_cap = need + need / 4;
             CU(cudaMalloc(&s->d_tiles, s->tiles_cap * sizeof(int2)));
         }
-        const bool homog = kernel == 3 && !s->sc.uniform_radius;
         if (homog)
             if (int rc = build_homog_copy(s)) return rc;
         CU(cudaMemsetAsync(s->d_tile_ctrl, 0, 2 * sizeof(int), s->stream));
         for (int part = 0; part < 2; part++) // full tiles first, partly filled ones last
             LAUNCH(s, build_tiles_kernel, div_up(s->ncell, 256), 256, 0, s->cell_start, s->ncell, s->sc.x_off,
-                   s->sc.x_off + s->sc.x_cells - 1, s->sc.dims[1] * s->sc.dims[2], s->d_tiles, s->d_tile_ctrl, part);
-        if (kernel == 3) { // persistent grid: 5 CTAs of 4 independent warps per SM (96 registers per thread)
+                   s->sc.x_off + s->sc.x_cells - 1, s->sc.dims[1] * s->sc.dims[2], s->d_tiles, s->d_tile_ctrl, part,
+                   tile_i);
+        if (kernel == 3) { // persistent grid: 8 (per-type radii) or 6 (uniform radius) CTAs of 4 independent warps per SM
             // experiment knob (cf_set_option "t4_ctas_per_sm"): fewer resident CTAs, enforced with dynamic shared memory
-            const int ctas = s->opt_t4_ctas > 0 ? std::min(s->opt_t4_ctas, T4_MINB) : T4_MINB;
+            const int minb = t4_minb(t4_ipt(homog ? 1 : 0));
+            const int ctas = s->opt_t4_ctas > 0 ? std::min(s->opt_t4_ctas, minb) : minb;
             const int grid = s->sm_count * ctas;
-            const size_t pad = ctas < T4_MINB ? (size_t)(220 * 1024 / ctas) - 36 * 1024 : 0;
+            const size_t pad = ctas < minb ? (size_t)(220 * 1024 / ctas) - 36 * 1024 : 0;
             if (pad) {
                 cudaFuncSetAttribute(force_tile4_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad);
                 cudaFuncSetAttribute(force_tile4_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad);

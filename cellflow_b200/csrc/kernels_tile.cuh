@@ -104,19 +104,19 @@ __global__ void count_tests_kernel(const int* __restrict__ cell_start, int ncell
 // depend on the order.
 __global__ void build_tiles_kernel(const int* __restrict__ cell_start, int ncell, int first_cell_x,
                                    int last_cell_x, int cells_per_x, int2* __restrict__ tiles,
-                                   int* __restrict__ ctrl, int part) {
+                                   int* __restrict__ ctrl, int part, int tile_i) {
     int cell = blockIdx.x * blockDim.x + threadIdx.x;
     if (cell >= ncell) return;
     int cx = cell / cells_per_x;
     if (cx < first_cell_x || cx > last_cell_x) return; // ghost layers are never i-cells
     int n = cell_start[cell + 1] - cell_start[cell];
     if (n <= 0) return;
-    const int nfull = n / TK_TI;
+    const int nfull = n / tile_i; // particles per tile: 128 (generation 3, generation 4) or 32 * T4_IPT
     if (part == 0) {
         if (nfull == 0) return;
         int base = atomicAdd(&ctrl[0], nfull);
         for (int k = 0; k < nfull; k++) tiles[base + k] = make_int2(cell, k);
-    } else if (n > nfull * TK_TI) {
+    } else if (n > nfull * tile_i) {
         int base = atomicAdd(&ctrl[0], 1);
         tiles[base] = make_int2(cell, nfull);
     }

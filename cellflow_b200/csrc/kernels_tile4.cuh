@@ -34,28 +34,38 @@
 #pragma once
 #include "kernels_tile.cuh"
 
+// Layers of 32 i per tile (= i particles per lane) and resident CTAs per SM, per mode.  Round 1 used 4 layers
+// (96 registers, 5 CTAs) to amortise the shared-memory reads of a quad over 4 blocks; with the box prefilter dead
+// quads are never read (LSU 12-19 % busy), and the kernel is latency / issue bound at 5 warps per scheduler, so
+// fewer layers = fewer registers = more resident warps wins (A/B profiles/r02_force_kernel_history.md):
+//   per-type radii (MODE 1): 1 layer, 64 registers, 8 CTAs;  uniform radius (MODE 0): 2 layers, 80 registers, 6 CTAs.
+#ifndef T4_IPT_MODE0
+#define T4_IPT_MODE0 2
+#endif
+#ifndef T4_IPT_MODE1
+#define T4_IPT_MODE1 1
+#endif
+__host__ __device__ constexpr int t4_ipt(int mode) { return mode ? T4_IPT_MODE1 : T4_IPT_MODE0; }
+__host__ __device__ constexpr int t4_minb(int ipt) { return ipt <= 1 ? 8 : (ipt == 2 ? 6 : 5); }
 #ifndef T4_WARPS
 #define T4_WARPS 4
 #endif
 #ifndef T4_PAIRSKIP
 #define T4_PAIRSKIP 0
 #endif
-#ifndef T4_MINB
-#define T4_MINB 5 // resident CTAs per SM the register budget is set for (96 registers per thread)
-#endif
 #define T4_JC 128 // staged j per chunk and warp: one quad of 4 consecutive j per lane
 #define T4_MAXSUB (TK_MAX_RUNS * CF_T_MAX)
 #define T4_INF __int_as_float(0x7f800000)
 
-template <int MODE>
+template <int MODE, int IPT>
 struct T4Shared {
     float x[T4_WARPS][2][T4_JC];
     float y[T4_WARPS][2][T4_JC];
     float z[T4_WARPS][2][T4_JC];
     int t[T4_WARPS][2][T4_JC];                       // MODE 0: byte offset of j's row in s_fv
     int2 sub[T4_WARPS][MODE ? T4_MAXSUB : TK_MAX_RUNS]; // [j0, j1) of every (sub-)run
-    float4 cst[MODE ? T4_WARPS : 1][4][32];          // MODE 1: (c2, A, B, cut2) of (layer, lane) for the current sub-run
-    float4 box[T4_WARPS][4][2];                      // (lo.xyz, prefilter threshold), (hi.xyz, -) of every layer
+    float4 cst[MODE ? T4_WARPS : 1][IPT][32];          // MODE 1: (c2, A, B, cut2) of (layer, lane) for the current sub-run
+    float4 box[T4_WARPS][IPT][2];                      // (lo.xyz, prefilter threshold), (hi.xyz, -) of every layer
     unsigned long long bar[T4_WARPS][2];             // STAGE 1: one mbarrier per (warp, stage buffer)
 };
 
@@ -171,17 +181,19 @@ __device__ __forceinline__ void t4_live(u64 dxa, u64 dya, u64 dza, u64 d2a, u64 
 // All live (layer, quad) blocks of one staged chunk.  MODE 0 takes the uniform threshold and derives
 // the table address from the packed types; MODE 1 reads (c2, A, B, cut2) of (layer, lane) from
 // shared memory per block.
-template <int MODE, bool WRAP, bool COUNT>
-__device__ __forceinline__ void t4_chunk(unsigned sbase, const unsigned (&live)[TK_IPT], const float (&npx)[TK_IPT],
-                                         const float (&npy)[TK_IPT], const float (&npz)[TK_IPT], unsigned tis4,
+template <int MODE, bool WRAP, bool COUNT, int IPT>
+__device__ __forceinline__ void t4_chunk(unsigned sbase, const unsigned (&live)[IPT], const float (&npx)[IPT],
+                                         const float (&npy)[IPT], const float (&npz)[IPT], unsigned tis4,
                                          unsigned s_tab_addr, unsigned cst_addr, float sx, float sy,
                                          float sz, float cutu, float c2u, float pau, float pbu,
-                                         T4AccScalar (&acc)[TK_IPT], int (&cnt)[TK_IPT], unsigned& n_tested,
+                                         T4AccScalar (&acc)[IPT], int (&cnt)[IPT], unsigned& n_tested,
                                          unsigned& n_live) {
     const u64 sx2 = tk_pack(sx, sx), sy2 = tk_pack(sy, sy), sz2 = tk_pack(sz, sz);
     constexpr unsigned STRIDE = T4_WARPS * 2 * T4_JC * 4; // bytes between the x, y, z, t arrays
     // live[k] bit q = (quad q, layer k) passed the box prefilter; quads with no live layer cost nothing
-    unsigned any = live[0] | live[1] | live[2] | live[3];
+    unsigned any = 0;
+#pragma unroll
+    for (int k = 0; k < IPT; k++) any |= live[k];
 #pragma unroll 1
     while (any) {
         const unsigned bit = any & (0u - any);
@@ -198,7 +210,7 @@ __device__ __forceinline__ void t4_chunk(unsigned sbase, const unsigned (&live)[
         const u64 ya = tk_pack(Y.x, Y.y), yb = tk_pack(Y.z, Y.w);
         const u64 za = tk_pack(Z.x, Z.y), zb = tk_pack(Z.z, Z.w);
 #pragma unroll
-        for (int k = 0; k < TK_IPT; k++) {
+        for (int k = 0; k < IPT; k++) {
             // MODE 0: layers whose box is not near skip the exact test (warp-uniform branch).  MODE 1 tests
             // every layer of a live quad: there the extra branch costs more than the tests it saves
             // (measured: eater 4.89 -> 4.76 ms without it, pulser 1.96 -> 2.30 ms without it)
@@ -242,15 +254,16 @@ __device__ __forceinline__ void t4_chunk(unsigned sbase, const unsigned (&live)[
 //          next 128-j chunk in with three 512-byte cp.async.bulk copies that complete on the warp's mbarrier
 //          (UBLKCP), no register round trip, no transpose; chunk starts are aligned down to 4 elements (16 bytes)
 //          and the elements in front of the sub-run are masked.  A/B in profiles/r02_staging_ab.md.
-template <int MODE, bool COUNT = false, int STAGE = 0>
-__global__ void __launch_bounds__(T4_WARPS * 32, T4_MINB)
+template <int MODE, bool COUNT = false, int STAGE = 0, int IPT = t4_ipt(MODE)>
+__global__ void __launch_bounds__(T4_WARPS * 32, t4_minb(IPT))
 force_tile4_kernel(const float4* __restrict__ pos4, const int* __restrict__ cell_start,
                    const float4* __restrict__ posj, const int* __restrict__ startj,
                    const int2* __restrict__ tiles, int* __restrict__ ctrl, float4* __restrict__ frc4, StepConst c,
                    const DeviceTables* __restrict__ tables, unsigned long long* __restrict__ block_counts = nullptr,
                    const float* __restrict__ jx = nullptr, const float* __restrict__ jy = nullptr,
                    const float* __restrict__ jz = nullptr) {
-    __shared__ __align__(16) T4Shared<MODE> sm;
+    __shared__ __align__(16) T4Shared<MODE, IPT> sm;
+    constexpr int T4_TI = 32 * IPT;
     // MODE 0: s_tab[tj*T + ti] = fv.  MODE 1: s_tab4[tj*T + ti] = (c2, fv*rep, -fv*att/Reff, cut2)
     __shared__ __align__(16) float s_tab[CF_TT_MAX * (MODE ? 4 : 1)];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -298,8 +311,8 @@ force_tile4_kernel(const float4* __restrict__ pos4, const int* __restrict__ cell
     int split = 1;
     if (tail > 0) {
         const float c1 = 1.0f;
-        const float c2 = 0.5f * 1.08f * (float)((2 * tail + nwarps - 1) / nwarps);
-        const float c4 = 0.25f * 1.22f * (float)((4 * tail + nwarps - 1) / nwarps);
+        const float c2 = IPT >= 2 ? 0.5f * 1.08f * (float)((2 * tail + nwarps - 1) / nwarps) : 1e9f;
+        const float c4 = IPT >= 4 ? 0.25f * 1.22f * (float)((4 * tail + nwarps - 1) / nwarps) : 1e9f;
         split = (c2 < c1 && c2 <= c4) ? 2 : ((c4 < c1 && c4 < c2) ? 4 : 1);
     }
     const int nvirtual = full + tail * split;
@@ -310,17 +323,17 @@ force_tile4_kernel(const float4* __restrict__ pos4, const int* __restrict__ cell
         if (lane == 0) tile = atomicAdd(&ctrl[1], 1);
         tile = __shfl_sync(0xffffffffu, tile, 0);
         if (tile >= nvirtual) break;
-        int first_layer = 0, max_i = TK_TI;
+        int first_layer = 0, max_i = T4_TI;
         if (tile >= full) { // a sub-tile of a tail tile
             const int v = tile - full;
             tile = full + v / split;
-            max_i = TK_TI / split;
-            first_layer = (v % split) * (TK_IPT / split);
+            max_i = T4_TI / split;
+            first_layer = (v % split) * (IPT / split);
         }
         const int2 tl = tiles[tile];
         const int cell = tl.x;
         const int cz = cell % nz, cy = (cell / nz) % ny, cx = cell / (nz * ny);
-        const int i_begin = cell_start[cell] + tl.y * TK_TI + 32 * first_layer;
+        const int i_begin = cell_start[cell] + tl.y * T4_TI + 32 * first_layer;
         const int ni = min(cell_start[cell + 1] - i_begin, max_i);
         if (ni <= 0) continue; // this part of the tile holds no particle
 
@@ -373,12 +386,12 @@ force_tile4_kernel(const float4* __restrict__ pos4, const int* __restrict__ cell
         }
 
         // ---- my i particles: layer k holds slots i_begin + 32k + lane ----
-        float npx[TK_IPT], npy[TK_IPT], npz[TK_IPT];
+        float npx[IPT], npy[IPT], npz[IPT];
         unsigned tis4 = 0; // byte k = 4 * type of this lane's particle in layer k
-        T4AccScalar acc[TK_IPT];
-        int cnt[TK_IPT];
+        T4AccScalar acc[IPT];
+        int cnt[IPT];
 #pragma unroll
-        for (int k = 0; k < TK_IPT; k++) {
+        for (int k = 0; k < IPT; k++) {
             const int il = k * 32 + lane;
             const bool v = il < ni;
             const float4 p = v ? pos4[i_begin + il] : make_float4(-TK_FAR, -TK_FAR, -TK_FAR, 0.f);
@@ -511,7 +524,7 @@ force_tile4_kernel(const float4* __restrict__ pos4, const int* __restrict__ cell
                     const int tj = csi - r * T;
                     const char* row = reinterpret_cast<const char*>(s_tab) + tj * (T * 16);
 #pragma unroll
-                    for (int k = 0; k < TK_IPT; k++) {
+                    for (int k = 0; k < IPT; k++) {
                         float4 e = *reinterpret_cast<const float4*>(row + ((tis4 >> (8 * k)) & 255u) * 4u);
                         if (!(k * 32 + lane < ni)) e.w = 0.f; // no particle: never accepts
                         asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(cst_addr + 512u * k), "f"(e.x), "f"(e.y), "f"(e.z), "f"(e.w) : "memory");
@@ -522,21 +535,24 @@ force_tile4_kernel(const float4* __restrict__ pos4, const int* __restrict__ cell
                 }
             }
             // ---- box prefilter: every lane tests its own quad against the box of each layer ----
-            unsigned live[TK_IPT];
+            unsigned live[IPT];
 #pragma unroll
-            for (int k = 0; k < TK_IPT; k++) {
+            for (int k = 0; k < IPT; k++) {
                 const float4 b0 = sm.box[warp][k][0], b1 = sm.box[warp][k][1]; // broadcast reads
                 const float gx = fmaxf(fmaxf((lox - b1.x) + sx, (b0.x - hix) - sx), 0.f);
                 const float gy = fmaxf(fmaxf((loy - b1.y) + sy, (b0.y - hiy) - sy), 0.f);
                 const float gz = fmaxf(fmaxf((loz - b1.z) + sz, (b0.z - hiz) - sz), 0.f);
                 live[k] = __ballot_sync(0xffffffffu, fmaf(gz, gz, fmaf(gx, gx, gy * gy)) < b0.w);
             }
-            if (live[0] | live[1] | live[2] | live[3]) {
+            unsigned any_live = 0;
+#pragma unroll
+            for (int k = 0; k < IPT; k++) any_live |= live[k];
+            if (any_live) {
                 if (wrap)
-                    t4_chunk<MODE, true, COUNT>(sbase, live, npx, npy, npz, tis4, s_tab_addr, cst_addr, sx, sy, sz, cutu, c2u,
+                    t4_chunk<MODE, true, COUNT, IPT>(sbase, live, npx, npy, npz, tis4, s_tab_addr, cst_addr, sx, sy, sz, cutu, c2u,
                                                 pau, pbu, acc, cnt, n_tested, n_live);
                 else
-                    t4_chunk<MODE, false, COUNT>(sbase, live, npx, npy, npz, tis4, s_tab_addr, cst_addr, sx, sy, sz, cutu, c2u,
+                    t4_chunk<MODE, false, COUNT, IPT>(sbase, live, npx, npy, npz, tis4, s_tab_addr, cst_addr, sx, sy, sz, cutu, c2u,
                                                  pau, pbu, acc, cnt, n_tested, n_live);
             }
             buf ^= 1; // the other buffer was last read one chunk ago by this same warp
@@ -545,7 +561,7 @@ force_tile4_kernel(const float4* __restrict__ pos4, const int* __restrict__ cell
 
         // ---- write back: the particle itself was tested too (d = 0, force term exactly 0) ----
 #pragma unroll
-        for (int k = 0; k < TK_IPT; k++) {
+        for (int k = 0; k < IPT; k++) {
             const int il = k * 32 + lane;
             if (il < ni) {
                 const float3 f = acc[k].sum();
