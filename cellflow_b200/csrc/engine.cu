@@ -147,6 +147,8 @@ struct cf_sim {
     int* h_cell_of = nullptr;
     float4* h_pos = nullptr;
     float* h_xyz[3] = {nullptr, nullptr, nullptr}; // the same copy as SoA planes (bulk-copy staging)
+    float4* d_qbox = nullptr;                      // STAGE 2: bounding boxes of the aligned quads of the j array
+    size_t qbox_cap = 0;
     uint32_t* h_comp = nullptr;
     size_t homog_cap = 0;
     int* h_start = nullptr;
@@ -712,6 +714,7 @@ extern "C" int cf_destroy(cf_sim* s) {
     }
     cudaFree(s->h_cell_of);
     cudaFree(s->h_pos);
+    cudaFree(s->d_qbox);
     for (int a = 0; a < 3; a++) cudaFree(s->h_xyz[a]);
     cudaFree(s->h_comp);
     cudaFree(s->h_start);
@@ -1073,7 +1076,7 @@ static int build_homog_copy(cf_sim* s) {
     int src = 0;
     if (int rc = radix_sort_pairs(s, s->hk, s->hv, nslots, (long long)nrow * s->T + 1, &src, d_nslots)) return rc;
     LAUNCH(s, homog_gather_kernel, div_up(nslots, 256), 256, 0, s->hk[src], s->hv[src], pos, s->h_cell_of, nz, nslots,
-           d_nslots, s->h_pos, s->h_comp, s->opt_t4_stage ? s->h_xyz[0] : nullptr, s->h_xyz[1], s->h_xyz[2]);
+           d_nslots, s->h_pos, s->h_comp, s->opt_t4_stage == 1 ? s->h_xyz[0] : nullptr, s->h_xyz[1], s->h_xyz[2]);
     LAUNCH(s, homog_bounds_kernel, div_up(nkeys + 1, 256), 256, 0, s->h_comp, nslots, d_nslots, s->h_start, nkeys);
     return 0;
 }
@@ -1157,7 +1160,30 @@ static int launch_force(cf_sim* s) {
                 s->block_counts_valid = true;
                 return 0;
             }
-            if (homog && s->opt_t4_stage)
+            if (s->opt_t4_stage == 2) {
+                // quad boxes of the j array the kernel streams: the type-sorted copy (element e), or the sorted slots
+                const float4* jarr = homog ? s->h_pos : pos;
+                const int upper = s->slab ? s->cap : s->n;
+                const size_t nq = (size_t)upper / 4 + 2;
+                if (nq > s->qbox_cap) {
+                    CU(cudaStreamSynchronize(s->stream));
+                    cudaFree(s->d_qbox);
+                    s->d_qbox = nullptr;
+                    s->qbox_cap = nq + nq / 8;
+                    CU(cudaMalloc(&s->d_qbox, s->qbox_cap * 2 * sizeof(float4)));
+                }
+                const int* d_cnt = s->slab ? s->d_slab + SLAB_NSLOTS : nullptr;
+                const int* d_first = (s->slab && !homog) ? s->d_slab + SLAB_FIRST : nullptr; // the copy starts at element 0
+                LAUNCH(s, quad_box_kernel, div_up(upper / 4 + 1, 256), 256, 0, jarr, 0, d_first, upper, d_cnt, s->d_qbox);
+                if (homog)
+                    LAUNCH(s, (force_tile4_kernel<1, false, 2>), grid, T4_WARPS * 32, pad, pos, s->cell_start, s->h_pos, s->h_start,
+                           s->d_tiles, s->d_tile_ctrl, s->frc, s->sc, s->d_tables, nullptr, nullptr, nullptr, nullptr, s->d_qbox);
+                else
+                    LAUNCH(s, (force_tile4_kernel<0, false, 2>), grid, T4_WARPS * 32, pad, pos, s->cell_start, pos, s->cell_start,
+                           s->d_tiles, s->d_tile_ctrl, s->frc, s->sc, s->d_tables, nullptr, nullptr, nullptr, nullptr, s->d_qbox);
+                return 0;
+            }
+            if (homog && s->opt_t4_stage == 1)
                 LAUNCH(s, (force_tile4_kernel<1, false, 1>), grid, T4_WARPS * 32, pad, pos, s->cell_start, s->h_pos, s->h_start,
                        s->d_tiles, s->d_tile_ctrl, s->frc, s->sc, s->d_tables, nullptr, s->h_xyz[0], s->h_xyz[1], s->h_xyz[2]);
             else if (homog)
@@ -1217,7 +1243,7 @@ static std::vector<char> step_signature(const cf_sim* s) {
     const void* ptrs[] = {s->pos[0], s->pos[1], s->vel[0], s->vel[1], s->id[0], s->id[1], s->frc, s->keys[0],
                           s->keys[1], s->vals[0], s->vals[1], s->hist, s->cell_start, s->d_tiles, s->d_tile_ctrl,
                           s->d_tables, s->d_half, s->hk[0], s->hk[1], s->hv[0], s->hv[1], s->h_cell_of, s->h_pos,
-                          s->h_comp, s->h_start, s->h_xyz[0], s->h_xyz[1], s->h_xyz[2]};
+                          s->h_comp, s->h_start, s->h_xyz[0], s->h_xyz[1], s->h_xyz[2], s->d_qbox};
     put(ptrs, sizeof(ptrs));
     int ints[] = {s->n, s->ncell, s->cur, s->opt_force_kernel, s->sorted_valid ? 1 : 0, s->half_bound_ok ? 1 : 0,
                   s->planned_force_kernel, s->opt_t4_ctas, s->opt_count_blocks, s->opt_t4_stage};

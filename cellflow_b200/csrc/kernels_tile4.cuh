@@ -254,6 +254,10 @@ __device__ __forceinline__ void t4_chunk(unsigned sbase, const unsigned (&live)[
 //          next 128-j chunk in with three 512-byte cp.async.bulk copies that complete on the warp's mbarrier
 //          (UBLKCP), no register round trip, no transpose; chunk starts are aligned down to 4 elements (16 bytes)
 //          and the elements in front of the sub-run are masked.  A/B in profiles/r02_staging_ab.md.
+// STAGE 2: the bounding boxes of all aligned quads of the j array are computed ONCE per step (quad_box_kernel,
+//          32 B per 4 j); a chunk then starts with one 32-byte load per lane and the box prefilter, and only the
+//          lanes whose quad survived load and stage their 4 positions — a dead chunk (about half of them) costs
+//          ~35 instructions instead of ~100, and its positions are never read.
 template <int MODE, bool COUNT = false, int STAGE = 0, int IPT = t4_ipt(MODE)>
 __global__ void __launch_bounds__(T4_WARPS * 32, t4_minb(IPT))
 force_tile4_kernel(const float4* __restrict__ pos4, const int* __restrict__ cell_start,
@@ -261,7 +265,7 @@ force_tile4_kernel(const float4* __restrict__ pos4, const int* __restrict__ cell
                    const int2* __restrict__ tiles, int* __restrict__ ctrl, float4* __restrict__ frc4, StepConst c,
                    const DeviceTables* __restrict__ tables, unsigned long long* __restrict__ block_counts = nullptr,
                    const float* __restrict__ jx = nullptr, const float* __restrict__ jy = nullptr,
-                   const float* __restrict__ jz = nullptr) {
+                   const float* __restrict__ jz = nullptr, const float4* __restrict__ qbox = nullptr) {
     __shared__ __align__(16) T4Shared<MODE, IPT> sm;
     constexpr int T4_TI = 32 * IPT;
     // MODE 0: s_tab[tj*T + ti] = fv.  MODE 1: s_tab4[tj*T + ti] = (c2, fv*rep, -fv*att/Reff, cut2)
@@ -282,7 +286,7 @@ force_tile4_kernel(const float4* __restrict__ pos4, const int* __restrict__ cell
         }
     }
     unsigned bar_addr = 0, bar_phase = 0; // STAGE 1: this warp's two mbarriers (+ 8 * buffer), their parity bits
-    if (STAGE) {
+    if (STAGE == 1) {
         bar_addr = (unsigned)__cvta_generic_to_shared(&sm.bar[warp][0]);
         if (lane == 0) {
             t4_mbar_init(bar_addr, 1);
@@ -427,7 +431,7 @@ force_tile4_kernel(const float4* __restrict__ pos4, const int* __restrict__ cell
     } while (0)
         T4_ADVANCE();
         int cur_si = -1, buf = 0;
-        if (STAGE && have && lane == 0) { // first chunk of the tile: three plane copies onto buffer 0's barrier
+        if (STAGE == 1 && have && lane == 0) { // first chunk of the tile: three plane copies onto buffer 0's barrier
             t4_mbar_expect(bar_addr, 3 * T4_JC * 4);
             t4_bulk_load(stage_addr, jx + off, T4_JC * 4, bar_addr);
             t4_bulk_load(stage_addr + STRIDE, jy + off, T4_JC * 4, bar_addr);
@@ -440,7 +444,14 @@ force_tile4_kernel(const float4* __restrict__ pos4, const int* __restrict__ cell
             // ---- load and publish the chunk: lane l holds the quad j = coff + 4l .. 4l+3 ----
             const unsigned sbase = stage_addr + (unsigned)buf * (T4_JC * 4);
             float lox = T4_INF, loy = T4_INF, loz = T4_INF, hix = -T4_INF, hiy = -T4_INF, hiz = -T4_INF;
-            if (STAGE) {
+            if (STAGE == 2) {
+                // precomputed box of my aligned quad (elements of a neighbouring sub-run only make it larger)
+                const int j0 = coff + 4 * lane;
+                if (j0 + 3 >= clo && j0 < cend) {
+                    const float4 bl = qbox[2 * (j0 >> 2)], bh = qbox[2 * (j0 >> 2) + 1];
+                    lox = bl.x, loy = bl.y, loz = bl.z, hix = bh.x, hiy = bh.y, hiz = bh.z;
+                }
+            } else if (STAGE == 1) {
                 // the chunk was requested one iteration ago: wait for its bytes, then every lane reads its own quad
                 while (!t4_mbar_try(bar_addr + 8u * (unsigned)buf, (bar_phase >> buf) & 1u)) {}
                 bar_phase ^= 1u << buf;
@@ -494,7 +505,12 @@ force_tile4_kernel(const float4* __restrict__ pos4, const int* __restrict__ cell
             }
             __syncwarp();
             T4_ADVANCE();
-            if (STAGE) {
+            if (STAGE == 2) {
+                if (have && lane < 8) { // the next chunk's 32 quad boxes: 1 KiB = 8 lines
+                    const float4* pf = qbox + 2 * (off >> 2) + min(8 * lane, 2 * ((end - 1 - off) >> 2)); // inside the array
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(pf));
+                }
+            } else if (STAGE == 1) {
                 // the next chunk (possibly of the next sub-run) -> the other buffer, which this warp finished
                 // reading one chunk ago (the __syncwarp above orders those reads before the request)
                 if (have && lane == 0) {
@@ -547,6 +563,28 @@ force_tile4_kernel(const float4* __restrict__ pos4, const int* __restrict__ cell
             unsigned any_live = 0;
 #pragma unroll
             for (int k = 0; k < IPT; k++) any_live |= live[k];
+            if (STAGE == 2 && any_live) {
+                // stage the surviving quads only (t4_chunk never reads the others)
+                if ((any_live >> lane) & 1u) {
+                    float4 q[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const int j = coff + 4 * lane + u;
+                        q[u] = (j >= clo && j < cend) ? posj[j] : make_float4(TK_FAR, TK_FAR, TK_FAR, 0.f);
+                    }
+                    const unsigned a = sbase + 16u * (unsigned)lane;
+                    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a), "f"(q[0].x), "f"(q[1].x), "f"(q[2].x), "f"(q[3].x) : "memory");
+                    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a + STRIDE), "f"(q[0].y), "f"(q[1].y), "f"(q[2].y), "f"(q[3].y) : "memory");
+                    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a + 2 * STRIDE), "f"(q[0].z), "f"(q[1].z), "f"(q[2].z), "f"(q[3].z) : "memory");
+                    if (MODE == 0) {
+                        const int rb = T * 4; // bytes per tj row of s_tab
+                        asm volatile("st.shared.v4.s32 [%0], {%1,%2,%3,%4};" ::"r"(a + 3 * STRIDE),
+                                     "r"((int)__float_as_uint(q[0].w) * rb), "r"((int)__float_as_uint(q[1].w) * rb),
+                                     "r"((int)__float_as_uint(q[2].w) * rb), "r"((int)__float_as_uint(q[3].w) * rb) : "memory");
+                    }
+                }
+                __syncwarp();
+            }
             if (any_live) {
                 if (wrap)
                     t4_chunk<MODE, true, COUNT, IPT>(sbase, live, npx, npy, npz, tis4, s_tab_addr, cst_addr, sx, sy, sz, cutu, c2u,
@@ -637,4 +675,27 @@ __global__ void homog_bounds_kernel(const uint32_t* __restrict__ comp, int nslot
         if (comp[mid] < (uint32_t)e) lo = mid + 1; else hi = mid;
     }
     startj[e] = lo;
+}
+
+// Bounding boxes of the aligned quads of a j array (STAGE 2): qbox[2q] = min xyz, qbox[2q+1] = max xyz of elements
+// 4q .. 4q+3 inside [first, first + count) (empty box when none is).  One thread per quad.
+__global__ void quad_box_kernel(const float4* __restrict__ posj, int first_host, const int* __restrict__ d_first,
+                                int count_upper, const int* __restrict__ d_count, float4* __restrict__ qbox) {
+    const int first = d_first ? *d_first : first_host;
+    const int count = d_count ? min(*d_count, count_upper) : count_upper;
+    const int q = (first >> 2) + blockIdx.x * blockDim.x + threadIdx.x;
+    if (4 * q >= first + count) return;
+    float lx = T4_INF, ly = T4_INF, lz = T4_INF, hx = -T4_INF, hy = -T4_INF, hz = -T4_INF;
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+        const int j = 4 * q + u;
+        if (j >= first && j < first + count) {
+            const float4 p = posj[j];
+            lx = fminf(lx, p.x), hx = fmaxf(hx, p.x);
+            ly = fminf(ly, p.y), hy = fmaxf(hy, p.y);
+            lz = fminf(lz, p.z), hz = fmaxf(hz, p.z);
+        }
+    }
+    qbox[2 * q] = make_float4(lx, ly, lz, 0.f);
+    qbox[2 * q + 1] = make_float4(hx, hy, hz, 0.f);
 }

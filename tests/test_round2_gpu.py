@@ -208,15 +208,17 @@ def test_block_counters_of_the_tile_kernel():
     sim.close()
 
 
-def test_bulk_copy_staging_is_bit_identical():
-    """Option "t4_stage" = 1: the j chunks of the type-sorted copy arrive through cp.async.bulk + mbarrier from SoA
-    planes (chunk starts aligned down to 16 bytes, foreign elements masked) instead of LDG -> registers -> STS.
-    Same pairs in the same order: counts and forces are bit-identical to the default staging, and match the oracle."""
+@pytest.mark.parametrize("stage", [1, 2])
+def test_alternative_chunk_staging_is_bit_identical(stage):
+    """Option "t4_stage": 1 = the j chunks of the type-sorted copy arrive through cp.async.bulk + mbarrier from SoA
+    planes; 2 = quad bounding boxes precomputed once per step, positions loaded for surviving quads only.  Both align
+    chunk starts down to 4 elements and mask foreign elements.  Same pairs in the same order: counts and forces are
+    bit-identical to the default staging, and match the oracle."""
     sim, p, table, radio, state, counts = small_sim(n=60000, kernel=3)
     sim.simulate(steps=2)
     a, ac = sim.getParticleData(), sim.getNeighborCounts()
     sim.setParticleData(state, counts)
-    sim.setOption("t4_stage", 1)
+    sim.setOption("t4_stage", stage)
     sim.simulate(steps=2)
     b, bc = sim.getParticleData(), sim.getNeighborCounts()
     assert sim.stats().force_kernel == 3
@@ -228,3 +230,28 @@ def test_bulk_copy_staging_is_bit_identical():
     assert np.array_equal(gcnt, wcnt)
     assert U.force_rel_err(got["acc"], want["acc"], fabs, U.force_multiplier_of(p, wcnt, counts)).max() <= U.FORCE_RTOL
     sim.close()
+    if stage == 2:   # uniform radius (the other instantiation) + a slab-mode run with ghost slots
+        p2, table2, radio2 = U.config("pulser", canvasWidth=3000.0, canvasHeight=3000.0, canvasDepth=3000.0)
+        st2, c2 = U.random_state(50000, 6, 19, p2.canvas, "uniform")
+        for slab in (False, True):
+            sim = cf.ParticleSimulation(0 if slab else len(st2), 6, init=False)
+            sim.params = U.to_lib_params(p2)
+            sim.setRadioByType(radio2)
+            sim.setForceTable(table2)
+            sim.setOption("force_kernel", 3)
+            sim.setOption("t4_stage", 2)
+            if slab:
+                sim.commInit(0, 1, 70000)
+                sim.uploadOwned(st2, c2, np.arange(len(st2), dtype=np.int32))
+            else:
+                sim.setParticleData(st2, c2)
+            sim.simulate()
+            if slab:
+                pp, cc, ii = sim.downloadOwned()
+                gcnt = np.zeros(len(st2), np.int32)
+                gcnt[ii] = cc
+            else:
+                gcnt = sim.getNeighborCounts()
+            _, wcnt, _ = O.step(st2, c2, p2, table2, radio2, "cells", THREADS)
+            assert np.array_equal(gcnt, wcnt), f"slab={slab}"
+            sim.close()
