@@ -518,13 +518,14 @@ def measure_multi(spec, args, steps, warmup, with_e2e):
         one_step()
     sim.sync()
     sim.statsReset()
-    cfd.barrier()
-    torch.cuda.synchronize()
-    with ClockSampler(local) as clocks:
+    with ClockSampler(local) as clocks:  # (NVML start-up takes tens of ms and differs per rank: before the barrier)
+        torch.cuda.synchronize()
+        cfd.barrier()
         t0 = time.perf_counter()
         for _ in range(steps):
             _lib.check(L.cf_bench_flush_l2_async(sim._h, C.c_size_t(L2_FLUSH)))
             one_step()
+        host_enqueue_ms = (time.perf_counter() - t0) / steps * 1e3  # host time to enqueue a step (must stay below the device time)
         sim.sync()
         torch.cuda.synchronize()
         cfd.barrier()
@@ -546,6 +547,7 @@ def measure_multi(spec, args, steps, warmup, with_e2e):
             {"step": round(my_ms, 4), "force": round(st.ms_force / k, 4), "sort": round(st.ms_sort / k, 4),
              "wait_migrants": round(st.ms_exchange_migrants / k, 4), "wait_halo": round(st.ms_exchange_halo / k, 4),
              "integrate": round(st.ms_integrate / k, 4), "graph": round(graph_ms / steps, 4),
+             "host_enqueue": round(host_enqueue_ms, 4),
              "sm_mhz": clocks.summary()["sm_mhz"], "reasons": clocks.summary()["reasons"]}).encode())])
     if with_e2e:
         # e2e: every rank round-trips what it owns through PINNED host memory each step

@@ -105,7 +105,7 @@ def main():
     table = O.force_table(raw, 6, p.forceRange, p.forceBias, p.forceOffset)
     state = O.init_particles(100_000, 6, 0x5EED0002, cf.INIT_SPAWN_CUBE, p.canvas)
     run_case("spawn-cube-100k", p, table, radio, state, np.zeros(len(state), np.int32), 4, None, rank, world, balanced=True)
-    p, table, radio = U.config("pulser", delta_t=0.9)
+    p, table, radio = U.config("pulser", delta_t=0.3)   # (dense blobs accelerate hard: a step must stay below one slab width)
     state, counts = U.random_state(80_000, 6, 37, p.canvas, "blobs", vel_scale=40.0)
     if world * cfd.interaction_radius(U.to_lib_params(p), radio) * 1.002 <= p.canvasWidth:
         run_case("blobs-80k", p, table, radio, state, counts, 4, (200.0, 5), rank, world, balanced=True)
