@@ -45,7 +45,9 @@ static void slab_update_geom(cf_sim* s) {
 // global count over the ranks, else the capacity), capped at a few waves of the device.
 static int slab_grid(const cf_sim* s) {
     const long long expect = s->n_total > 0 ? std::min<long long>(s->cap_own, s->n_total / s->world + 1) : s->cap_own;
-    return (int)std::max<long long>(1, std::min<long long>((expect + 255) / 256, (long long)s->sm_count * 32));
+    // (every block of an emitting kernel ends with a fence + a ticket atomic on one word: a few blocks per SM, not
+    //  one per 256 particles — 3,900 tickets cost 25 us of the slab integrate at 1 M particles)
+    return (int)std::max<long long>(1, std::min<long long>((expect + 255) / 256, (long long)s->sm_count * 8));
 }
 
 static SlabPeers slab_peers(const cf_sim* s) {
