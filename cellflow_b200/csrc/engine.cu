@@ -1076,7 +1076,7 @@ static int build_homog_copy(cf_sim* s) {
     int src = 0;
     if (int rc = radix_sort_pairs(s, s->hk, s->hv, nslots, (long long)nrow * s->T + 1, &src, d_nslots)) return rc;
     LAUNCH(s, homog_gather_kernel, div_up(nslots, 256), 256, 0, s->hk[src], s->hv[src], pos, s->h_cell_of, nz, nslots,
-           d_nslots, s->h_pos, s->h_comp, s->opt_t4_stage == 1 ? s->h_xyz[0] : nullptr, s->h_xyz[1], s->h_xyz[2]);
+           d_nslots, s->h_pos, s->h_comp, (s->opt_t4_stage == 1 || s->opt_t4_stage == 3) ? s->h_xyz[0] : nullptr, s->h_xyz[1], s->h_xyz[2]);
     LAUNCH(s, homog_bounds_kernel, div_up(nkeys + 1, 256), 256, 0, s->h_comp, nslots, d_nslots, s->h_start, nkeys);
     return 0;
 }
@@ -1183,7 +1183,10 @@ static int launch_force(cf_sim* s) {
                            s->d_tiles, s->d_tile_ctrl, s->frc, s->sc, s->d_tables, nullptr, nullptr, nullptr, nullptr, s->d_qbox);
                 return 0;
             }
-            if (homog && s->opt_t4_stage == 1)
+            if (homog && s->opt_t4_stage == 3)
+                LAUNCH(s, (force_tile4_kernel<1, false, 3>), grid, T4_WARPS * 32, pad, pos, s->cell_start, s->h_pos, s->h_start,
+                       s->d_tiles, s->d_tile_ctrl, s->frc, s->sc, s->d_tables, nullptr, s->h_xyz[0], s->h_xyz[1], s->h_xyz[2]);
+            else if (homog && s->opt_t4_stage == 1)
                 LAUNCH(s, (force_tile4_kernel<1, false, 1>), grid, T4_WARPS * 32, pad, pos, s->cell_start, s->h_pos, s->h_start,
                        s->d_tiles, s->d_tile_ctrl, s->frc, s->sc, s->d_tables, nullptr, s->h_xyz[0], s->h_xyz[1], s->h_xyz[2]);
             else if (homog)

@@ -208,10 +208,11 @@ def test_block_counters_of_the_tile_kernel():
     sim.close()
 
 
-@pytest.mark.parametrize("stage", [1, 2])
+@pytest.mark.parametrize("stage", [1, 2, 3])
 def test_alternative_chunk_staging_is_bit_identical(stage):
     """Option "t4_stage": 1 = the j chunks of the type-sorted copy arrive through cp.async.bulk + mbarrier from SoA
-    planes; 2 = quad bounding boxes precomputed once per step, positions loaded for surviving quads only.  Both align
+    planes; 2 = quad bounding boxes precomputed once per step, positions loaded for surviving quads only; 3 = SoA
+    planes through registers (no transposition, mask-free fast path).  All align
     chunk starts down to 4 elements and mask foreign elements.  Same pairs in the same order: counts and forces are
     bit-identical to the default staging, and match the oracle."""
     sim, p, table, radio, state, counts = small_sim(n=60000, kernel=3)
