@@ -547,7 +547,8 @@ def measure_multi(spec, args, steps, warmup, with_e2e):
             {"step": round(my_ms, 4), "force": round(st.ms_force / k, 4), "sort": round(st.ms_sort / k, 4),
              "wait_migrants": round(st.ms_exchange_migrants / k, 4), "wait_halo": round(st.ms_exchange_halo / k, 4),
              "integrate": round(st.ms_integrate / k, 4), "graph": round(graph_ms / steps, 4),
-             "host_enqueue": round(host_enqueue_ms, 4),
+             "host_enqueue": round(host_enqueue_ms, 4), "step_max": round(st.ms_step_max, 4),
+             "exchange_max_step": round(st.ms_exchange_max, 4),
              "sm_mhz": clocks.summary()["sm_mhz"], "reasons": clocks.summary()["reasons"]}).encode())])
     if with_e2e:
         # e2e: every rank round-trips what it owns through PINNED host memory each step

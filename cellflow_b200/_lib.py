@@ -108,6 +108,7 @@ class Stats(C.Structure):
         ("ms_graph_total", C.c_double), ("graph_builds", C.c_int64),
         ("ms_exchange_migrants", C.c_double), ("ms_exchange_halo", C.c_double),
         ("exact_tested_pairs", C.c_int64), ("evaluated_pair_lanes", C.c_int64),
+        ("ms_step_max", C.c_double), ("ms_exchange_max", C.c_double),
     ]
 
 

@@ -177,7 +177,7 @@ struct cf_sim {
     double wait_timeout_ms = 20000.0;
     double cell_edge = 1.0;        // cell edge and largest interaction radius of the current grid
     float rmax = 0.f;
-    double ms_exchange = 0, ms_exchange_mig = 0, ms_exchange_halo = 0;
+    double ms_exchange = 0, ms_exchange_mig = 0, ms_exchange_halo = 0, ms_exchange_max = 0, ms_step_max = 0;
 
     // CUDA graphs of the (static) single-GPU step sequence: small problems are launch-bound
     struct StepGraph {
@@ -1873,7 +1873,7 @@ extern "C" int cf_stats_reset(cf_sim* s) {
     CU(cudaStreamSynchronize(s->stream));
     s->ev_used = 0;
     s->ms_sort = s->ms_force = s->ms_integrate = s->ms_total = s->ms_graph = s->ms_exchange = 0;
-    s->ms_exchange_mig = s->ms_exchange_halo = 0;
+    s->ms_exchange_mig = s->ms_exchange_halo = s->ms_exchange_max = s->ms_step_max = 0;
     s->ms_graph_total = 0;
     s->graph_builds = 0;
     s->stat_steps = 0;
@@ -1903,9 +1903,11 @@ extern "C" int cf_get_stats(cf_sim* s, cf_stats* st) {
                 s->ms_exchange += x + y;
                 s->ms_exchange_mig += x;
                 s->ms_exchange_halo += y;
+                s->ms_exchange_max = std::max(s->ms_exchange_max, (double)(x + y));
             }
         }
         s->ms_total += a + b + c;
+        s->ms_step_max = std::max(s->ms_step_max, (double)(a + b + c));
         s->stat_steps++;
     }
     s->ev_used = 0;
@@ -1919,6 +1921,8 @@ extern "C" int cf_get_stats(cf_sim* s, cf_stats* st) {
     st->ms_exchange = s->ms_exchange;
     st->ms_exchange_migrants = s->ms_exchange_mig;
     st->ms_exchange_halo = s->ms_exchange_halo;
+    st->ms_exchange_max = s->ms_exchange_max;
+    st->ms_step_max = s->ms_step_max;
     st->steps = s->stat_steps;
     st->launches = s->launches;
     for (int a = 0; a < 3; a++) st->grid[a] = s->sc.dims[a];

@@ -133,6 +133,8 @@ typedef struct cf_stats {
     double ms_exchange_halo;     /* slab mode, part of ms_exchange: halo pack + wait + ghost unpack + ghost bounds */
     int64_t exact_tested_pairs;  /* tile kernel, option "count_blocks": pairs that reached the exact per-pair test */
     int64_t evaluated_pair_lanes;/* tile kernel, option "count_blocks": pair-lanes whose force terms were evaluated */
+    double ms_step_max;          /* slowest single step since cf_stats_reset (timing != 0) */
+    double ms_exchange_max;      /* slab mode: largest ms_exchange of a single step (a spike = one late neighbour) */
 } cf_stats;
 
 typedef struct cf_sim cf_sim;
