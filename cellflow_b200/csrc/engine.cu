@@ -6,6 +6,7 @@
 //     cell key -> stable radix sort -> reorder -> cell bounds -> pair force -> fused integrate
 // with no host synchronisation inside (the reference synchronises after every launch, .cu:553).
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h> // header-only NVTX 3: ranges around the phases of a step
 
 #include <algorithm>
 #include <cmath>
@@ -175,6 +176,7 @@ struct cf_sim {
     bool mig_sent = false;         // the last integrate already emitted this step's migrants
     long long n_total = 0;         // global particle count (slab mode)
     double wait_timeout_ms = 20000.0;
+    double opt_min_layer_width = 0.0; // slab mode: lower bound of the x layer width (same on every rank)
     double cell_edge = 1.0;        // cell edge and largest interaction radius of the current grid
     float rmax = 0.f;
     double ms_exchange = 0, ms_exchange_mig = 0, ms_exchange_halo = 0, ms_exchange_max = 0, ms_step_max = 0;
@@ -212,6 +214,12 @@ struct cf_sim {
     long long launches = 0;
     long long tested_pairs = 0;
     int last_force_kernel = 0;
+};
+
+// NVTX range for the lifetime of the object (a few ns when no profiler is attached).
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
 };
 
 #define LAUNCH(sim, kernel, grid, block, smem, ...)                         \
@@ -407,7 +415,9 @@ static float compute_tables(cf_sim* s, DeviceTables& t, bool& uniform) {
 
 // x layers of a slab of width w (same rule on every rank, for every rank's slab)
 static int slab_layers(const cf_sim* s, double w) {
-    int nxl = std::max(1, std::min((int)floor(w / s->cell_edge), 1022));
+    // option "slab_min_layer_width": wider x layers = wider ghost layers, for a proximity-graph distance larger than
+    // the interaction radius (the graph may not reach further than one ghost layer)
+    int nxl = std::max(1, std::min((int)floor(w / std::max(s->cell_edge, s->opt_min_layer_width)), 1022));
     while (nxl > 1 && w / nxl < (double)s->rmax * (1.0 + 4.0 * nxl * 1.1920929e-7)) nxl--;
     return nxl;
 }
@@ -1220,11 +1230,17 @@ static int launch_force(cf_sim* s) {
 static int step_direct(cf_sim* s, StepEvents* ev) {
     if (ev) CU(cudaEventRecord(ev->e[0], s->stream));
     if (ev) ev->has_exchange = s->slab && !s->sorted_valid;
-    if (int rc = build_cell_list(s, ev ? &ev->e[4] : nullptr)) return rc;
+    {
+        NvtxRange r("cellflow:cell_list_build");
+        if (int rc = build_cell_list(s, ev ? &ev->e[4] : nullptr)) return rc;
+    }
     if (ev) CU(cudaEventRecord(ev->e[1], s->stream));
-    if (s->n > 0 || s->slab)
+    if (s->n > 0 || s->slab) {
+        NvtxRange r("cellflow:pair_force");
         if (int rc = launch_force(s)) return rc;
+    }
     if (ev) CU(cudaEventRecord(ev->e[2], s->stream));
+    NvtxRange r_int("cellflow:integrate");
     if (s->slab) {
         // fused integrate + migrant emission: the leavers go straight into the neighbours' mailboxes
         s->seq_mig++;
@@ -1624,6 +1640,7 @@ extern "C" int cf_build_graph(cf_sim* s, float dist, int max_conn, int* n_edges)
         CU(cudaMalloc(&s->edge_slots, sizeof(int2) * (size_t)need));
         s->edge_cap = (int)need;
     }
+    NvtxRange r_graph("cellflow:proximity_graph");
     fold_graph_timing(s);
     cudaEvent_t* gev = s->opt_timing ? next_graph_events(s) : nullptr;
     if (gev) CU(cudaEventRecord(gev[0], s->stream));
@@ -1862,6 +1879,7 @@ extern "C" int cf_set_option(cf_sim* s, const char* name, double value) {
     else if (k == "halo_capacity") s->cap_halo = (int)value;       // before cf_comm_init, same on every rank
     else if (k == "migrant_capacity") s->cap_mig = (int)value;     // before cf_comm_init, same on every rank
     else if (k == "wait_timeout_ms") s->wait_timeout_ms = value;
+    else if (k == "slab_min_layer_width") s->opt_min_layer_width = value;
     else return fail(CF_ERR_ARG, "unknown option '%s'", name);
     s->sorted_valid = false, s->state_gen++;
     return CF_OK;

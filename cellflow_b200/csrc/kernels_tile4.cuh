@@ -50,9 +50,6 @@ __host__ __device__ constexpr int t4_minb(int ipt) { return ipt <= 1 ? 8 : (ipt 
 #ifndef T4_WARPS
 #define T4_WARPS 4
 #endif
-#ifndef T4_PAIRSKIP
-#define T4_PAIRSKIP 0
-#endif
 #define T4_JC 128 // staged j per chunk and warp: one quad of 4 consecutive j per lane
 #define T4_MAXSUB (TK_MAX_RUNS * CF_T_MAX)
 #define T4_INF __int_as_float(0x7f800000)
@@ -215,10 +212,6 @@ __device__ __forceinline__ void t4_chunk(unsigned sbase, const unsigned (&live)[
             // every layer of a live quad: there the extra branch costs more than the tests it saves
             // (measured: eater 4.89 -> 4.76 ms without it, pulser 1.96 -> 2.30 ms without it)
             if (MODE == 0 && !(live[k] & bit)) continue;
-#if T4_PAIRSKIP
-            // MODE 1: one warp-uniform branch per PAIR of layers (half the branches of the per-layer form)
-            if (MODE == 1 && !((live[k & ~1] | live[k | 1]) & bit)) continue;
-#endif
             float4 cs = make_float4(c2u, pau, pbu, cutu);
             if (MODE == 1) // (c2, A, B, cut2) of (layer k, this lane): 32-bit shared address, no generic pointer
                 asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(cs.x), "=f"(cs.y), "=f"(cs.z), "=f"(cs.w) : "r"(cst_addr + 512u * k));

@@ -303,6 +303,8 @@ int cf_download_cell_keys(cf_sim* sim, uint32_t* keys, int32_t* ids, int capacit
  *   "global_particle_count", "halo_capacity", "migrant_capacity"
  *                    slab mode, the same on every rank: grid sizing / mailbox capacities (before cf_comm_init)
  *   "wait_timeout_ms"  slab mode: how long a rank waits for a neighbour's message before it reports an error
+ *   "slab_min_layer_width"  slab mode, the same on every rank: x layers (and with them the ghost layers) at least
+ *                    this wide — set it to the proximity-graph distance when that exceeds the interaction radius
  * Unknown names return CF_ERR_ARG. */
 int cf_set_option(cf_sim* sim, const char* name, double value);
 /* Measurement helpers for bench.py (not on the simulation path): live FP32 FMA peak of the

@@ -17,7 +17,8 @@ import oracle as O  # noqa: E402
 import util as U  # noqa: E402
 
 
-def run_case(name, p, table, radio, state, counts, steps, graph, rank, world, balanced=False):
+def run_case(name, p, table, radio, state, counts, steps, graph, rank, world, balanced=False, capacity_factor=1.5,
+             options=None):
     import torch.distributed as dist
     n = len(state)
     lp = U.to_lib_params(p)
@@ -25,7 +26,10 @@ def run_case(name, p, table, radio, state, counts, steps, graph, rank, world, ba
     if balanced:  # clustered state: equal-count slabs from the x histogram, every slab >= one interaction radius
         hist, _ = np.histogram(state["pos"][:, 0], bins=4096, range=(0.0, float(p.canvasWidth)))
         bounds = cfd.balanced_bounds(hist, p.canvasWidth, world, cfd.interaction_radius(lp, radio) * 1.002)
-    sim, rank, world = cfd.make_slab_sim(lp, None, radio, n, None, cf.INIT_UNIFORM, force_table=table, bounds=bounds)
+    sim, rank, world = cfd.make_slab_sim(lp, None, radio, n, None, cf.INIT_UNIFORM, force_table=table, bounds=bounds,
+                                         capacity_factor=capacity_factor)
+    for k, v in (options or {}).items():
+        sim.setOption(k, v)
     mine, mcounts, ids = cfd.partition(state, counts, p.canvasWidth, rank, world, bounds)
     sim.uploadOwned(mine, mcounts, ids)
     want_state, want_counts = state, counts
@@ -109,6 +113,21 @@ def main():
     state, counts = U.random_state(80_000, 6, 37, p.canvas, "blobs", vel_scale=40.0)
     if world * cfd.interaction_radius(U.to_lib_params(p), radio) * 1.002 <= p.canvasWidth:
         run_case("blobs-80k", p, table, radio, state, counts, 4, (200.0, 5), rank, world, balanced=True)
+    # E. ranks that own nothing: every particle starts in the first half of rank 0's slab (uniform bounds, capacity for
+    #    all of them on one rank); the empty ranks still take part in every exchange
+    p, table, radio = U.config("pulser", delta_t=0.5)
+    state, counts = U.random_state(40_000, 6, 41, p.canvas, "uniform", vel_scale=30.0)
+    state["pos"][:, 0] *= np.float32(0.5 / world)
+    run_case("one-rank-owns-all-40k", p, table, radio, state, counts, 3, (200.0, 5), rank, world,
+             capacity_factor=1.2 * world)
+    # F. a graph distance larger than the interaction radius: option "slab_min_layer_width" widens the x layers (and
+    #    the ghost layers with them) so that the rule's 200 fits — the sparse case C with the graph on
+    p = O.Params()
+    raw, radio = O.default_tables(6)
+    table = O.force_table(raw, 6, p.forceRange, p.forceBias, p.forceOffset)
+    state, counts = U.random_state(100_000, 6, 43, p.canvas, "uniform", vel_scale=300.0)
+    run_case("default-100k-graph-wider-layers", p, table, radio, state, counts, 2, (200.0, 5), rank, world,
+             options={"slab_min_layer_width": 200.5})
     if rank == 0:
         assert mig > 0, "test did not exercise migration"
         print(f"DIST_CHECK_OK world={world} migrated={mig}", flush=True)
