@@ -1161,7 +1161,13 @@ static int launch_force(cf_sim* s) {
             }
             if (s->opt_count_blocks) { // instrumented build: exact-tested and evaluated (layer, quad) blocks
                 CU(cudaMemsetAsync(s->d_block_counts, 0, 2 * sizeof(unsigned long long), s->stream));
-                if (homog)
+                if (homog && s->opt_t4_stage == 4)
+                    LAUNCH(s, (force_tile4_kernel<1, true, 4>), grid, T4_WARPS * 32, pad, pos, s->cell_start, s->h_pos, s->h_start,
+                           s->d_tiles, s->d_tile_ctrl, s->frc, s->sc, s->d_tables, s->d_block_counts);
+                else if (s->opt_t4_stage == 4)
+                    LAUNCH(s, (force_tile4_kernel<0, true, 4>), grid, T4_WARPS * 32, pad, pos, s->cell_start, pos, s->cell_start,
+                           s->d_tiles, s->d_tile_ctrl, s->frc, s->sc, s->d_tables, s->d_block_counts);
+                else if (homog)
                     LAUNCH(s, (force_tile4_kernel<1, true>), grid, T4_WARPS * 32, pad, pos, s->cell_start, s->h_pos, s->h_start,
                            s->d_tiles, s->d_tile_ctrl, s->frc, s->sc, s->d_tables, s->d_block_counts);
                 else
@@ -1191,6 +1197,15 @@ static int launch_force(cf_sim* s) {
                 else
                     LAUNCH(s, (force_tile4_kernel<0, false, 2>), grid, T4_WARPS * 32, pad, pos, s->cell_start, pos, s->cell_start,
                            s->d_tiles, s->d_tile_ctrl, s->frc, s->sc, s->d_tables, nullptr, nullptr, nullptr, nullptr, s->d_qbox);
+                return 0;
+            }
+            if (s->opt_t4_stage == 4) { // live quads stored compacted (kernels_tile4.cuh, STAGE 4)
+                if (homog)
+                    LAUNCH(s, (force_tile4_kernel<1, false, 4>), grid, T4_WARPS * 32, pad, pos, s->cell_start, s->h_pos, s->h_start,
+                           s->d_tiles, s->d_tile_ctrl, s->frc, s->sc, s->d_tables, nullptr);
+                else
+                    LAUNCH(s, (force_tile4_kernel<0, false, 4>), grid, T4_WARPS * 32, pad, pos, s->cell_start, pos, s->cell_start,
+                           s->d_tiles, s->d_tile_ctrl, s->frc, s->sc, s->d_tables, nullptr);
                 return 0;
             }
             if (homog && s->opt_t4_stage == 3)

@@ -241,8 +241,77 @@ __device__ __forceinline__ void t4_chunk(unsigned sbase, const unsigned (&live)[
     }
 }
 
+// The same blocks, for a chunk whose LIVE quads were stored COMPACTED (STAGE 4): quad r of the list sits at
+// sbase + 16 r, r = 0 .. nq-1, in lane order (= the order t4_chunk walks them, so the summation order and every
+// result bit are the same).  The loop is a running shared address: no bit scan (BREV + FLO are XU-pipe
+// instructions, 16 cycles of the pipe the 8 MUFU of a live block need), no address arithmetic.
+// clive[k] bit r = layer k passed the box prefilter for quad r (only read by MODE 0 with more than one layer).
+template <int MODE, bool WRAP, bool COUNT, int IPT>
+__device__ __forceinline__ void t4_chunk_compact(unsigned sbase, unsigned nq, const unsigned (&clive)[IPT],
+                                                 const float (&npx)[IPT], const float (&npy)[IPT],
+                                                 const float (&npz)[IPT], unsigned tis4, unsigned s_tab_addr,
+                                                 unsigned cst_addr, float sx, float sy, float sz, float cutu, float c2u,
+                                                 float pau, float pbu, T4AccScalar (&acc)[IPT], int (&cnt)[IPT],
+                                                 unsigned& n_tested, unsigned& n_live) {
+    const u64 sx2 = tk_pack(sx, sx), sy2 = tk_pack(sy, sy), sz2 = tk_pack(sz, sz);
+    constexpr unsigned STRIDE = T4_WARPS * 2 * T4_JC * 4; // bytes between the x, y, z, t arrays
+    unsigned qa = sbase;
+    const unsigned qe = sbase + 16u * nq;
+    unsigned bit = 1u;
+#pragma unroll 1
+    do {
+        float4 X, Y, Z;
+        int4 Tq = make_int4(0, 0, 0, 0);
+        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(X.x), "=f"(X.y), "=f"(X.z), "=f"(X.w) : "r"(qa));
+        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(Y.x), "=f"(Y.y), "=f"(Y.z), "=f"(Y.w) : "r"(qa + STRIDE));
+        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(Z.x), "=f"(Z.y), "=f"(Z.z), "=f"(Z.w) : "r"(qa + 2 * STRIDE));
+        if (MODE == 0)
+            asm volatile("ld.shared.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(Tq.x), "=r"(Tq.y), "=r"(Tq.z), "=r"(Tq.w) : "r"(qa + 3 * STRIDE));
+        const u64 xa = tk_pack(X.x, X.y), xb = tk_pack(X.z, X.w);
+        const u64 ya = tk_pack(Y.x, Y.y), yb = tk_pack(Y.z, Y.w);
+        const u64 za = tk_pack(Z.x, Z.y), zb = tk_pack(Z.z, Z.w);
+#pragma unroll
+        for (int k = 0; k < IPT; k++) {
+            if (MODE == 0 && IPT > 1 && !(clive[k] & bit)) continue; // as t4_chunk: MODE 1 tests every layer of a live quad
+            float4 cs = make_float4(c2u, pau, pbu, cutu);
+            if (MODE == 1)
+                asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(cs.x), "=f"(cs.y), "=f"(cs.z), "=f"(cs.w) : "r"(cst_addr + 512u * k));
+            const u64 px = tk_pack(npx[k], npx[k]), py = tk_pack(npy[k], npy[k]), pz = tk_pack(npz[k], npz[k]);
+            u64 dxa = tk_add2(xa, px), dxb = tk_add2(xb, px);
+            u64 dya = tk_add2(ya, py), dyb = tk_add2(yb, py);
+            u64 dza = tk_add2(za, pz), dzb = tk_add2(zb, pz);
+            if (WRAP) {
+                dxa = tk_add2(dxa, sx2), dxb = tk_add2(dxb, sx2);
+                dya = tk_add2(dya, sy2), dyb = tk_add2(dyb, sy2);
+                dza = tk_add2(dza, sz2), dzb = tk_add2(dzb, sz2);
+            }
+            const u64 d2a = tk_fma2(dza, dza, tk_fma2(dxa, dxa, tk_mul2(dya, dya)));
+            const u64 d2b = tk_fma2(dzb, dzb, tk_fma2(dxb, dxb, tk_mul2(dyb, dyb)));
+            float a0, a1, b0, b1;
+            tk_unpack(d2a, a0, a1);
+            tk_unpack(d2b, b0, b1);
+            const float mn = fminf(fminf(a0, a1), fminf(b0, b1));
+            if (COUNT) n_tested++;
+            if (__any_sync(0xffffffffu, mn < cs.w)) {
+                if (COUNT) n_live++;
+                const unsigned fva = s_tab_addr + ((tis4 >> (8 * k)) & 255u);
+                t4_live<MODE>(dxa, dya, dza, d2a, dxb, dyb, dzb, d2b, a0, a1, b0, b1, cs.w, cs.x, cs.y, cs.z, fva, Tq,
+                              acc[k], cnt[k]);
+            }
+        }
+        qa += 16u;
+        if (MODE == 0 && IPT > 1) bit <<= 1;
+    } while (qa != qe);
+}
+
 // STAGE 0: the j chunk goes global -> registers (4 x LDG.128 per lane) -> shared (3-4 x STS.128, transposed to
 //          SoA), next chunk hinted into L1.
+// STAGE 4: as STAGE 0, but the box prefilter runs on the registers BEFORE anything is stored, and only the quads
+//          it lets through are stored, compacted to the front of the staging buffer (rank = popc of the live mask
+//          below the lane): a dead chunk stores nothing, the block loop of a live one is a running address
+//          (t4_chunk_compact).  Loads use clamped indices (no per-element predicates, no default moves; the quad
+//          box of a partly valid quad is unaffected by the repeated last element), the invalid elements of the one
+//          partly valid quad are pushed out of range just before the store.  Bit-identical to STAGE 0.
 // STAGE 1 (MODE 1 only): the type-sorted copy also exists as SoA planes (jx, jy, jz); one elected lane brings the
 //          next 128-j chunk in with three 512-byte cp.async.bulk copies that complete on the warp's mbarrier
 //          (UBLKCP), no register round trip, no transpose; chunk starts are aligned down to 4 elements (16 bytes)
@@ -303,6 +372,7 @@ force_tile4_kernel(const float4* __restrict__ pos4, const int* __restrict__ cell
     const unsigned s_tab_addr = (unsigned)__cvta_generic_to_shared(s_tab);
     const unsigned stage_addr = (unsigned)__cvta_generic_to_shared(&sm.x[warp][0][0]); // + buf*256 + 4*slot
     constexpr unsigned STRIDE = T4_WARPS * 2 * T4_JC * 4;
+    const unsigned lane_lt = (1u << lane) - 1u; // STAGE 4: rank of a live quad = popc(live mask & lane_lt)
 
     // Tail: the tiles of the last, partly filled round (ntiles mod warps-of-the-grid) are handed out
     // as 2 or 4 sub-tiles of 2 or 1 layers when that shortens the round: a sub-tile costs its share
@@ -423,7 +493,7 @@ force_tile4_kernel(const float4* __restrict__ pos4, const int* __restrict__ cell
             if (++si >= nsub) { have = false; break; } \
             const int2 e_ = wsub[si];               \
             lo = e_.x, end = e_.y;                  \
-            off = STAGE ? (lo & ~3) : lo; /* bulk copies start on 16-byte boundaries */ \
+            off = (STAGE >= 1 && STAGE <= 3) ? (lo & ~3) : lo; /* bulk copies start on 16-byte boundaries */ \
         }                                           \
     } while (0)
         T4_ADVANCE();
@@ -437,6 +507,90 @@ force_tile4_kernel(const float4* __restrict__ pos4, const int* __restrict__ cell
         float sx = 0.f, sy = 0.f, sz = 0.f;
         bool wrap = false;
         while (have) {
+            if (STAGE == 4) {
+                const int csi = si, coff = off, cend = end;
+                if (csi != cur_si) { // a new (sub-)run: its minimum-image shift, MODE 1: its pair constants
+                    cur_si = csi;
+                    const int r = MODE ? csi / T : csi;
+                    const int code = __shfl_sync(0xffffffffu, r_code, r);
+                    sx = (code & 1) ? -c.W[0] : ((code & 2) ? c.W[0] : 0.f);
+                    sy = (code & 4) ? -c.W[1] : ((code & 8) ? c.W[1] : 0.f);
+                    sz = (code & 16) ? -c.W[2] : ((code & 32) ? c.W[2] : 0.f);
+                    wrap = code != 0;
+                    if (MODE == 1) {
+                        const int tj = csi - r * T;
+                        const char* row = reinterpret_cast<const char*>(s_tab) + tj * (T * 16);
+#pragma unroll
+                        for (int k = 0; k < IPT; k++) {
+                            float4 e = *reinterpret_cast<const float4*>(row + ((tis4 >> (8 * k)) & 255u) * 4u);
+                            if (!(k * 32 + lane < ni)) e.w = 0.f; // no particle: never accepts
+                            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(cst_addr + 512u * k), "f"(e.x), "f"(e.y), "f"(e.z), "f"(e.w) : "memory");
+                            const float mx = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(e.w))); // cut2 >= 0
+                            if (lane == 0) sm.box[warp][k][0].w = mx * 1.0001f + 0.01f;
+                        }
+                        __syncwarp();
+                    }
+                }
+                // ---- the chunk into registers: lane l holds the quad j = coff + 4l .. 4l+3 (clamped to the sub-run) ----
+                const int j0 = coff + 4 * lane, jl = cend - 1;
+                float4 q[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) q[u] = posj[min(j0 + u, jl)];
+                T4_ADVANCE();
+                if (have && lane < 17) { // the next chunk (possibly of the next run): prefetch hint, 2 KiB <= 17 lines
+                    const float4* pf = posj + min(off + 8 * lane, end - 1);
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(pf));
+                }
+                const float lox = fminf(fminf(q[0].x, q[1].x), fminf(q[2].x, q[3].x)), hix = fmaxf(fmaxf(q[0].x, q[1].x), fmaxf(q[2].x, q[3].x));
+                const float loy = fminf(fminf(q[0].y, q[1].y), fminf(q[2].y, q[3].y)), hiy = fmaxf(fmaxf(q[0].y, q[1].y), fmaxf(q[2].y, q[3].y));
+                const float loz = fminf(fminf(q[0].z, q[1].z), fminf(q[2].z, q[3].z)), hiz = fmaxf(fmaxf(q[0].z, q[1].z), fmaxf(q[2].z, q[3].z));
+                // ---- box prefilter on the registers; quads past the end of the sub-run are masked out ----
+                const int nvq = (cend - coff + 3) >> 2;
+                const unsigned vmask = nvq >= 32 ? 0xffffffffu : ((1u << nvq) - 1u);
+                unsigned live[IPT], any_live = 0;
+#pragma unroll
+                for (int k = 0; k < IPT; k++) {
+                    const float4 b0 = sm.box[warp][k][0], b1 = sm.box[warp][k][1]; // broadcast reads
+                    const float gx = fmaxf(fmaxf((lox - b1.x) + sx, (b0.x - hix) - sx), 0.f);
+                    const float gy = fmaxf(fmaxf((loy - b1.y) + sy, (b0.y - hiy) - sy), 0.f);
+                    const float gz = fmaxf(fmaxf((loz - b1.z) + sz, (b0.z - hiz) - sz), 0.f);
+                    live[k] = __ballot_sync(0xffffffffu, fmaf(gz, gz, fmaf(gx, gx, gy * gy)) < b0.w) & vmask;
+                    any_live |= live[k];
+                }
+                if (any_live) {
+                    const unsigned sbase = stage_addr + (unsigned)buf * (T4_JC * 4);
+                    // the repeated elements of the sub-run's last quad leave the range (selects that take the place of the
+                    // register moves of the transposition)
+                    const bool v1 = j0 + 1 < cend, v2 = j0 + 2 < cend, v3 = j0 + 3 < cend;
+                    const unsigned rank = (unsigned)__popc(any_live & lane_lt);
+                    if ((any_live >> lane) & 1u) {
+                        const unsigned a = sbase + 16u * rank;
+                        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a), "f"(q[0].x), "f"(v1 ? q[1].x : TK_FAR), "f"(v2 ? q[2].x : TK_FAR), "f"(v3 ? q[3].x : TK_FAR) : "memory");
+                        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a + STRIDE), "f"(q[0].y), "f"(v1 ? q[1].y : TK_FAR), "f"(v2 ? q[2].y : TK_FAR), "f"(v3 ? q[3].y : TK_FAR) : "memory");
+                        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a + 2 * STRIDE), "f"(q[0].z), "f"(v1 ? q[1].z : TK_FAR), "f"(v2 ? q[2].z : TK_FAR), "f"(v3 ? q[3].z : TK_FAR) : "memory");
+                        if (MODE == 0) {
+                            const int rb = T * 4; // bytes per tj row of s_tab
+                            asm volatile("st.shared.v4.s32 [%0], {%1,%2,%3,%4};" ::"r"(a + 3 * STRIDE),
+                                         "r"((int)__float_as_uint(q[0].w) * rb), "r"((int)__float_as_uint(q[1].w) * rb),
+                                         "r"((int)__float_as_uint(q[2].w) * rb), "r"((int)__float_as_uint(q[3].w) * rb) : "memory");
+                        }
+                    }
+                    unsigned clive[IPT];
+#pragma unroll
+                    for (int k = 0; k < IPT; k++) // MODE 0, > 1 layer: the per-layer masks in list order
+                        clive[k] = (MODE == 0 && IPT > 1) ? __reduce_or_sync(0xffffffffu, ((live[k] >> lane) & 1u) << rank) : 0u;
+                    __syncwarp();
+                    const unsigned nq = (unsigned)__popc(any_live);
+                    if (wrap)
+                        t4_chunk_compact<MODE, true, COUNT, IPT>(sbase, nq, clive, npx, npy, npz, tis4, s_tab_addr, cst_addr, sx, sy, sz,
+                                                                 cutu, c2u, pau, pbu, acc, cnt, n_tested, n_live);
+                    else
+                        t4_chunk_compact<MODE, false, COUNT, IPT>(sbase, nq, clive, npx, npy, npz, tis4, s_tab_addr, cst_addr, sx, sy, sz,
+                                                                  cutu, c2u, pau, pbu, acc, cnt, n_tested, n_live);
+                    buf ^= 1; // the other buffer was last read one chunk ago by this same warp
+                }
+                continue;
+            }
             const int csi = si, coff = off, cend = end, clo = lo;
             // ---- load and publish the chunk: lane l holds the quad j = coff + 4l .. 4l+3 ----
             const unsigned sbase = stage_addr + (unsigned)buf * (T4_JC * 4);

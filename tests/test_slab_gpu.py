@@ -108,3 +108,19 @@ def test_multi_rank_matches_single_gpu(world):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "DIST_CHECK_OK" in r.stdout
+
+
+def test_slab_capacity_overflow_is_reported_not_silent():
+    """A ghost layer (or the leavers) that does not fit its mailbox is truncated on the device, and the very next
+    synchronising call returns CF_ERR_CAPACITY — no host check in the step, no hang, no silent CF_OK (ADVICE r01:
+    the overflow used to surface one build late, after wrong forces had been returned)."""
+    p, table, radio = U.config("pulser")
+    state, counts = U.random_state(40000, 6, 3, p.canvas, "uniform")
+    sim = slab_sim(p, table, radio, state, counts, capacity=60000, halo_capacity=500)
+    with pytest.raises(cf.CellFlowError) as e:
+        sim.simulate()          # cf_step is asynchronous; cf_sync (inside simulate) reads the device's error word
+    assert e.value.code == -6 and "halo capacity" in str(e.value)
+    sim.close()
+    with pytest.raises(cf.CellFlowError) as e:     # fewer slots than particles: refused at upload
+        slab_sim(p, table, radio, state, counts, capacity=30000)
+    assert e.value.code == -6
