@@ -196,7 +196,10 @@ struct cf_sim {
     // options
     int opt_force_kernel = 0; // 0 auto, 1 per-particle, 2 tile (generation 3), 3 tile (generation 4)
     int opt_timing = 0;
-    int opt_t4_stage = 0;     // 1: j chunks staged with cp.async.bulk + mbarrier from SoA planes (per-type radii only)
+    int opt_t4_stage = 4;     // staging of the j chunks in the tile kernel (kernels_tile4.cuh): 4 (default) box prefilter on the
+                              // registers, live quads stored compacted; 0 every quad stored (round 1 .. mid round 2); 1
+                              // cp.async.bulk + mbarrier from SoA planes; 2 precomputed quad boxes; 3 SoA planes through registers
+                              // (1 and 3: per-type radii only).  All bit-identical.
     int opt_count_blocks = 0; // instrumented tile kernel: counts exact-tested / evaluated blocks (cf_stats)
     unsigned long long* d_block_counts = nullptr;
     bool block_counts_valid = false;
@@ -1158,6 +1161,8 @@ static int launch_force(cf_sim* s) {
             if (pad) {
                 cudaFuncSetAttribute(force_tile4_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad);
                 cudaFuncSetAttribute(force_tile4_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad);
+                cudaFuncSetAttribute(force_tile4_kernel<1, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad);
+                cudaFuncSetAttribute(force_tile4_kernel<0, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad);
             }
             if (s->opt_count_blocks) { // instrumented build: exact-tested and evaluated (layer, quad) blocks
                 CU(cudaMemsetAsync(s->d_block_counts, 0, 2 * sizeof(unsigned long long), s->stream));

@@ -47,6 +47,12 @@
 #endif
 __host__ __device__ constexpr int t4_ipt(int mode) { return mode ? T4_IPT_MODE1 : T4_IPT_MODE0; }
 __host__ __device__ constexpr int t4_minb(int ipt) { return ipt <= 1 ? 8 : (ipt == 2 ? 6 : 5); }
+#ifndef T4_PRED
+#define T4_PRED 1 // accepted pairs accumulated under predicates (0: integer accept masks, the round-1 form)
+#endif
+#ifndef T4_UNROLL
+#define T4_UNROLL 1
+#endif
 #ifndef T4_WARPS
 #define T4_WARPS 4
 #endif
@@ -140,6 +146,20 @@ struct T4AccScalar {
         tk_unpack(dzb, b0, b1);
         z = fmaf(s3, b1, fmaf(s2, b0, fmaf(s1, a1, fmaf(s0, a0, z))));
     }
+    // one pair under its accept predicate d2 < thr: force term and neighbour count (a rejected, padded or
+    // overflowed pair touches nothing)
+    __device__ __forceinline__ void add_if(float d2, float thr, float s, float dx, float dy, float dz, int& cnt) {
+        asm("{\n\t"
+            ".reg .pred p;\n\t"
+            "setp.lt.f32 p, %4, %5;\n\t"
+            "@p fma.rn.f32 %0, %6, %7, %0;\n\t"
+            "@p fma.rn.f32 %1, %6, %8, %1;\n\t"
+            "@p fma.rn.f32 %2, %6, %9, %2;\n\t"
+            "@p add.s32 %3, %3, 1;\n\t"
+            "}"
+            : "+f"(x), "+f"(y), "+f"(z), "+r"(cnt)
+            : "f"(d2), "f"(thr), "f"(s), "f"(dx), "f"(dy), "f"(dz));
+    }
     __device__ __forceinline__ float3 sum() const { return make_float3(x, y, z); }
 };
 
@@ -147,7 +167,6 @@ template <int MODE>
 __device__ __forceinline__ void t4_live(u64 dxa, u64 dya, u64 dza, u64 d2a, u64 dxb, u64 dyb, u64 dzb, u64 d2b,
                                         float a0, float a1, float b0, float b1, float thr, float c2, float pa,
                                         float pb, unsigned fv_base, int4 Tq, T4AccScalar& acc, int& cnt) {
-    const int m0 = t4_setlt(a0, thr), m1 = t4_setlt(a1, thr), m2 = t4_setlt(b0, thr), m3 = t4_setlt(b1, thr);
     const u64 eps = tk_pack(0.0001f, 0.0001f);
     const u64 xa = tk_add2(d2a, eps), xb = tk_add2(d2b, eps);
     const u64 c22 = tk_pack(c2, c2);
@@ -169,10 +188,26 @@ __device__ __forceinline__ void t4_live(u64 dxa, u64 dya, u64 dza, u64 d2a, u64 
     float s0, s1, s2, s3;
     tk_unpack(sa, s0, s1);
     tk_unpack(sb, s2, s3);
+#if T4_PRED
+    // accepted pairs only: the three FFMA and the count of a pair run under the predicate of its accept test
+    // (4 FSETP + 12 @P FFMA + 4 @P IADD; the mask form below needs 4 SEL + 4 LOP3 + 2 IADD3 more per block)
+    float x0, x1, x2, x3;
+    tk_unpack(dxa, x0, x1), tk_unpack(dxb, x2, x3);
+    float y0, y1, y2, y3;
+    tk_unpack(dya, y0, y1), tk_unpack(dyb, y2, y3);
+    float z0, z1, z2, z3;
+    tk_unpack(dza, z0, z1), tk_unpack(dzb, z2, z3);
+    acc.add_if(a0, thr, s0, x0, y0, z0, cnt);
+    acc.add_if(a1, thr, s1, x1, y1, z1, cnt);
+    acc.add_if(b0, thr, s2, x2, y2, z2, cnt);
+    acc.add_if(b1, thr, s3, x3, y3, z3, cnt);
+#else
+    const int m0 = t4_setlt(a0, thr), m1 = t4_setlt(a1, thr), m2 = t4_setlt(b0, thr), m3 = t4_setlt(b1, thr);
     sa = tk_pack(t4_and(s0, m0), t4_and(s1, m1));
     sb = tk_pack(t4_and(s2, m2), t4_and(s3, m3));
     cnt -= (m0 + m1) + (m2 + m3);
     acc.add(sa, sb, dxa, dya, dza, dxb, dyb, dzb);
+#endif
 }
 
 // All live (layer, quad) blocks of one staged chunk.  MODE 0 takes the uniform threshold and derives
@@ -258,7 +293,8 @@ __device__ __forceinline__ void t4_chunk_compact(unsigned sbase, unsigned nq, co
     unsigned qa = sbase;
     const unsigned qe = sbase + 16u * nq;
     unsigned bit = 1u;
-#pragma unroll 1
+    constexpr int UNROLL = T4_UNROLL;
+#pragma unroll UNROLL
     do {
         float4 X, Y, Z;
         int4 Tq = make_int4(0, 0, 0, 0);

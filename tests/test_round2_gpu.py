@@ -208,12 +208,13 @@ def test_block_counters_of_the_tile_kernel():
     sim.close()
 
 
-@pytest.mark.parametrize("stage", [1, 2, 3, 4])
+@pytest.mark.parametrize("stage", [0, 1, 2, 3])
 def test_alternative_chunk_staging_is_bit_identical(stage):
     """Option "t4_stage": 1 = the j chunks of the type-sorted copy arrive through cp.async.bulk + mbarrier from SoA
     planes; 2 = quad bounding boxes precomputed once per step, positions loaded for surviving quads only; 3 = SoA
-    planes through registers (no transposition, mask-free fast path); 4 = box prefilter on the registers, live quads
-    stored compacted.  1-3 align
+    planes through registers (no transposition, mask-free fast path); 0 = every quad stored, prefilter afterwards (the
+    default until the middle of round 2).  The default (4) runs the box prefilter on the registers and stores the live
+    quads compacted.  1-3 align
     chunk starts down to 4 elements and mask foreign elements.  Same pairs in the same order: counts and forces are
     bit-identical to the default staging, and match the oracle."""
     sim, p, table, radio, state, counts = small_sim(n=60000, kernel=3)
@@ -232,7 +233,7 @@ def test_alternative_chunk_staging_is_bit_identical(stage):
     assert np.array_equal(gcnt, wcnt)
     assert U.force_rel_err(got["acc"], want["acc"], fabs, U.force_multiplier_of(p, wcnt, counts)).max() <= U.FORCE_RTOL
     sim.close()
-    if stage in (2, 4):   # uniform radius (the other instantiation) + a slab-mode run with ghost slots
+    if stage in (0, 2):   # uniform radius (the other instantiation) + a slab-mode run with ghost slots
         p2, table2, radio2 = U.config("pulser", canvasWidth=3000.0, canvasHeight=3000.0, canvasDepth=3000.0)
         st2, c2 = U.random_state(50000, 6, 19, p2.canvas, "uniform")
         for slab in (False, True):
