@@ -1,27 +1,36 @@
 // kernels_tile4.cuh — pair-force kernel, generation 4 (the FP32-bound hot kernel).
 //
-// Same decomposition as kernels_tile.cuh (one WARP owns a tile of <= 128 particles of one cell as
-// 4 register-resident layers of 32; the 27 neighbour cells are streamed as <= 18 contiguous runs
+// Same decomposition as kernels_tile.cuh (one WARP owns a tile of 32 x IPT particles of one cell as
+// IPT register-resident layers of 32; the 27 neighbour cells are streamed as <= 18 contiguous runs
 // through a warp-private double buffer, 128 j per chunk; one warp vote per (layer, quad of 4 j)
 // gates the force terms), with what the round-1 ncu captures asked for
 // (profiles/r01_force_kernel_history.md):
 //
 //   * BOX PREFILTER.  The exact test of a (layer, quad) block costs 12 packed FP32 instructions
 //     = 24 FMA-pipe cycles per SM sub-partition, and 50-70% of the blocks are dead.  A chunk is
-//     128 staged j, one quad of 4 consecutive j per lane: each lane takes the bounding box of its
-//     own quad (no shuffles) and tests it against the bounding box of each layer's 32 i (4
-//     ballots per chunk).  The quad loop walks the quads with a live layer only (dead quads cost
+//     128 j, one quad of 4 consecutive j per lane: each lane takes the bounding box of its
+//     own quad (no shuffles) and tests it against the bounding box of each layer's 32 i (one
+//     ballot per layer and chunk).  The quad loop walks the quads with a live layer only (dead quads cost
 //     nothing); uniform radii (MODE 0) also skip the layers of a live quad whose own box is far,
 //     per-type radii (MODE 1) test all of them (the extra branch cost more than it saved there).
+//   * COMPACTED STAGING (STAGE 4, the default since the middle of round 2).  The prefilter runs on the
+//     registers the chunk was loaded into, and only the quads it lets through are stored to shared
+//     memory, packed to the front of the warp's buffer (rank = popc of the live mask below the lane).
+//     A dead chunk stores nothing; the block loop of a live one is a running shared address — no bit
+//     scan (BREV + FLO are XU-pipe instructions, the pipe the MUFU of the force terms need), 25
+//     instead of 30 instructions per exact-tested block.
+//   * PREDICATED ACCUMULATION.  The three FFMA and the count of a pair run under the predicate of its
+//     accept test (T4AccScalar::add_if): 36 instead of 42 instructions per live block.
 //   * TYPE-HOMOGENEOUS j RUNS for per-type radii (MODE 1).  The j stream comes from a second
-//     copy of the positions sorted by (xy row, type, z cell, Morton): inside a sub-run every j
+//     copy of the positions sorted by (xy row, type, z cell, Hilbert): inside a sub-run every j
 //     has the same type, so cut2 / force value / 1/Reff of a pair depend on the lane only and
 //     are fetched once per sub-run instead of once per pair; the vote test is the exact accept
 //     test.  The v3 kernel needed a float4 table gather and a second compare per evaluated pair.
-//   * LEANER FORCE PATH.  Accept bits as integer masks (set.lt.s32.f32): the neighbour count is
-//     two IADD3, the rejected pairs are zeroed with one AND on the bits of s (so a NaN/Inf of a
-//     padded or rejected pair can never leak); no generic-pointer arithmetic on shared memory.
-//   * 96 REGISTERS, 5 CTAs per SM: scalar force accumulators, layer boxes in shared memory, the
+//   * LEANER FORCE PATH.  A rejected, padded or overflowed pair touches neither the force nor the count
+//     (predicates; -DT4_PRED=0: integer accept masks, set.lt.s32.f32 + AND on the bits of s), so its
+//     NaN/Inf can never leak; no generic-pointer arithmetic on shared memory.
+//   * REGISTERS: 64 / 8 CTAs per SM (1 layer per tile, per-type radii), 80 / 6 (2 layers, uniform radius; round 1: 4
+//     layers, 96 registers, 5 CTAs): scalar force accumulators, layer boxes in shared memory, the
 //     next chunk prefetched into L1 by a hint instead of into registers (and across run
 //     boundaries); one code path for every tile occupancy (empty layers have empty boxes and
 //     positions at 1e30, so they are never live).
