@@ -220,8 +220,8 @@ graph_kernel(const float4* __restrict__ gpos, const uint32_t* __restrict__ gvals
 // path on almost every candidate for the whole warp (lanes accept different candidates), and its
 // per-thread serial scan is long.  Here the 32 lanes test 32 consecutive candidates at once
 // (coalesced loads), and the 2*maxConn smallest ids are kept in a list DISTRIBUTED OVER THE LANES
-// (lane r holds the r-th smallest id so far): inserting one accepted candidate is a ballot, a
-// popc and three shuffles, warp-uniform, no shared memory.  Same rule, same edge set.
+// (one entry per lane, unordered; the largest id kept is tracked with a warp reduction): inserting one
+// accepted candidate is a shuffle and a select, warp-uniform, no shared memory.  Same rule, same edge set.
 // ---------------------------------------------------------------------------------------------
 #define CF_GRAPHW_WARPS 4
 __global__ void __launch_bounds__(CF_GRAPHW_WARPS * 32)
@@ -240,9 +240,12 @@ graph_warp_kernel(const float4* __restrict__ gpos, const uint32_t* __restrict__ 
     const int K = 2 * max_conn; // <= 32: one list entry per lane
     const float4 p = gpos[q];
     const int my_id = __float_as_int(p.w);
+    // (type, cell): the type needs the one integer division; the cell coordinates are recomputed from the position
+    // with the key kernel's own expression (same floats, same result) instead of three more divisions
     const int t = (int)(key / (uint32_t)g.ncell);
-    const int cell = (int)(key - (uint32_t)t * (uint32_t)g.ncell);
-    const int cz = cell % g.dims[2], cy = (cell / g.dims[2]) % g.dims[1], cx = cell / (g.dims[2] * g.dims[1]);
+    const int cx = graph_coord(p.x, g.org[0], g.inv[0], g.dims[0]);
+    const int cy = graph_coord(p.y, g.org[1], g.inv[1], g.dims[1]);
+    const int cz = graph_coord(p.z, g.org[2], g.inv[2], g.dims[2]);
     const int z0 = max(cz - 1, 0), z1 = min(cz + 1, g.dims[2] - 1);
     const int tbase = t * g.ncell;
     // the <= 9 candidate ranges (one per (x, y) row; z-adjacent cells of a type are contiguous):
@@ -256,10 +259,12 @@ graph_warp_kernel(const float4* __restrict__ gpos, const uint32_t* __restrict__ 
             r_j1 = gstart[row + z1 + 1];
         }
     }
-    // distributed list, sorted by id: lane r < cnt holds the r-th smallest candidate id
+    // distributed list, UNORDERED: lane r < cnt holds one candidate (id, graph position).  While the list is not
+    // full a candidate goes to lane cnt; once it is full it replaces the largest id (lane kl), and the new largest
+    // id kth is one REDUX.MAX away — no shifting of a sorted list (round 1: a ballot, a popc and three shuffles up
+    // per insertion; 40 % of the kernel's instructions at the spawn cube of BASELINE config 2)
     int l_id = 0x7fffffff, l_q = 0;
-    float l_d2 = 0.f;
-    int cnt = 0, kth = 0x7fffffff; // kth = largest id kept when the list is full
+    int cnt = 0, kth = 0x7fffffff, kl = 0; // kth = largest id kept when the list is full, held by lane kl
     // chunks of 32 candidates over all rows; the next chunk is loaded before the current one is
     // processed (the kernel is bound by the latency of these loads and of the insertions)
     int row = -1, c0 = 0, end = 0;
@@ -292,26 +297,30 @@ graph_warp_kernel(const float4* __restrict__ gpos, const uint32_t* __restrict__ 
             acc &= acc - 1;
             const int c_id = __shfl_sync(0xffffffffu, jid, src);
             if (c_id >= kth) continue; // the list filled up meanwhile (warp-uniform)
-            const float c_d2 = __shfl_sync(0xffffffffu, d2, src);
-            const int pos = __popc(__ballot_sync(0xffffffffu, l_id < c_id)); // entries that stay in front
-            const int u_id = __shfl_up_sync(0xffffffffu, l_id, 1);
-            const int u_q = __shfl_up_sync(0xffffffffu, l_q, 1);
-            const float u_d2 = __shfl_up_sync(0xffffffffu, l_d2, 1);
-            if (lane == pos) l_id = c_id, l_q = base + src, l_d2 = c_d2;
-            else if (lane > pos) l_id = u_id, l_q = u_q, l_d2 = u_d2;
-            if (lane >= K) l_id = 0x7fffffff; // dropped: the largest id of a full list
+            if (lane == (cnt < K ? cnt : kl)) l_id = c_id, l_q = base + src;
             cnt = min(cnt + 1, K);
-            if (cnt == K) kth = __shfl_sync(0xffffffffu, l_id, K - 1);
+            if (cnt == K) { // full: the largest id kept and its lane
+                kth = __reduce_max_sync(0xffffffffu, lane < K ? l_id : (int)0x80000000);
+                kl = __ffs(__ballot_sync(0xffffffffu, lane < K && l_id == kth)) - 1;
+            }
         }
     }
 #undef GW_ADVANCE
     if (cnt == 0) return;
-    // stable sort by d2 (.cu:235-243): rank of entry r = entries with smaller d2, or equal d2 and
-    // smaller list position (the list is in index order, as the reference's scan produces it)
+    // distances of the kept candidates (same expression as the test above: bit-identical), then the stable sort by
+    // d2 (.cu:235-243) as a rank: entries with smaller d2, or equal d2 and smaller id (the reference's list is in
+    // index order = id order)
+    float l_d2 = 0.f;
+    if (lane < cnt) {
+        const float4 o = gpos[l_q];
+        const float dx = __fsub_rn(o.x, p.x), dy = __fsub_rn(o.y, p.y), dz = __fsub_rn(o.z, p.z);
+        l_d2 = cf_dist2(dx, dy, dz);
+    }
     int rank = 0;
     for (int b = 0; b < cnt; b++) {
         const float bd = __shfl_sync(0xffffffffu, l_d2, b);
-        rank += (bd < l_d2 || (bd == l_d2 && b < lane)) ? 1 : 0;
+        const int bi = __shfl_sync(0xffffffffu, l_id, b);
+        rank += (bd < l_d2 || (bd == l_d2 && bi < l_id)) ? 1 : 0;
     }
     const int w = min(cnt, max_conn);
     int base = 0;
