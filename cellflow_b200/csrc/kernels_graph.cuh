@@ -96,11 +96,20 @@ __global__ void graph_bounds_kernel(const uint32_t* __restrict__ skeys, int n_up
 // The per-thread candidate lists live in shared memory, laid out [entry][thread]: dynamic
 // indexing costs one conflict-free LDS/STS instead of a scattered local-memory transaction
 // per lane (the first version kept them in local memory and spent most of its time there).
+// The lists are UNORDERED: a candidate is appended, or replaces the largest id kept once the list is
+// full (that id and its position are found by one scan of the list whenever it changes while full), and
+// the final stable sort by d2 breaks ties by id (index order = id order).  The id-sorted insertion of
+// round 1 ran its shared-memory shift loop at 2 active lanes per instruction for 40 % of the kernel's
+// instructions (ncu, profiles/r02_graph_blocks_c5-settings-2M.txt): graph phase 1.09 -> 0.83 ms at
+// BASELINE config 5.
 // The lists are sized for the actual 2*maxConn (dynamic shared memory: 7.5 KB per CTA at the
 // default maxConn = 5, so 32 CTAs = all 64 warps of an SM are resident), and the candidate loop
 // keeps CF_GRAPH_BATCH independent 16-byte loads in flight: the kernel is bound by the latency
 // of those (L2-resident) loads, not by arithmetic.
 #define CF_GRAPH_THREADS 64
+#ifndef CF_GRAPH_APPEND
+#define CF_GRAPH_APPEND 1 // unordered candidate lists (0: id-sorted insertion, the round-1 form)
+#endif
 #define CF_GRAPH_BATCH 4
 struct GraphList {
     int* id;
@@ -124,6 +133,9 @@ graph_kernel(const float4* __restrict__ gpos, const uint32_t* __restrict__ gvals
                 reinterpret_cast<float*>(s_lists + 2 * K * CF_GRAPH_THREADS) + threadIdx.x};
     int q = blockIdx.x * blockDim.x + threadIdx.x;
     int ncand = 0, my_id = 0, my_slot = 0;
+#if CF_GRAPH_APPEND
+    int maxid = 0x7fffffff, maxpos = 0;
+#endif
     bool active = false;
     if (q < nq) {
         uint32_t key = gkeys[q];
@@ -158,6 +170,21 @@ graph_kernel(const float4* __restrict__ gpos, const uint32_t* __restrict__ gvals
                             float dx = __fsub_rn(o.x, p.x), dy = __fsub_rn(o.y, p.y), dz = __fsub_rn(o.z, p.z);
                             float d2 = cf_dist2(dx, dy, dz);
                             if (!(d2 < dist2)) continue;
+#if CF_GRAPH_APPEND
+                            // unordered list: append, or replace the largest id kept (maxid at maxpos) once it is full
+                            if (jid > maxid) continue;
+                            const int pos = ncand < K ? ncand++ : maxpos;
+                            L.I(pos) = jid;
+                            L.Q(pos) = j;
+                            L.D(pos) = d2;
+                            if (ncand == K) { // full: the largest id kept and where it sits
+                                maxid = L.I(0), maxpos = 0;
+                                for (int e = 1; e < K; e++) {
+                                    const int v = L.I(e);
+                                    if (v > maxid) maxid = v, maxpos = e;
+                                }
+                            }
+#else
                             if (ncand == K && jid > L.I(K - 1)) continue;
                             // insert into the id-sorted candidate list (drop the largest id when full)
                             int pos = ncand < K ? ncand : K - 1;
@@ -171,6 +198,7 @@ graph_kernel(const float4* __restrict__ gpos, const uint32_t* __restrict__ gvals
                             L.Q(pos) = j;
                             L.D(pos) = d2;
                             if (ncand < K) ncand++;
+#endif
                         }
                     }
                 }
@@ -180,7 +208,11 @@ graph_kernel(const float4* __restrict__ gpos, const uint32_t* __restrict__ gvals
                 float kd = L.D(a);
                 int ki = L.I(a), kq = L.Q(a);
                 int b = a - 1;
+#if CF_GRAPH_APPEND
+                while (b >= 0 && (L.D(b) > kd || (L.D(b) == kd && L.I(b) > ki))) { // ties: index order = id order
+#else
                 while (b >= 0 && L.D(b) > kd) {
+#endif
                     L.D(b + 1) = L.D(b);
                     L.I(b + 1) = L.I(b);
                     L.Q(b + 1) = L.Q(b);
