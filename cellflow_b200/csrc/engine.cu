@@ -1570,7 +1570,7 @@ static int graph_device_sequence(cf_sim* s, const GraphPlan& P, bool with_cell_l
                s->edge_cap, s->d_edge_count);
     else
         LAUNCH(s, graph_kernel, div_up(count, CF_GRAPH_THREADS), CF_GRAPH_THREADS,
-               (size_t)3 * 2 * P.mc * CF_GRAPH_THREADS * sizeof(int), s->gpos, s->gv[src], s->gk[src], s->gstart, count, d_n,
+               graph_list_bytes(P.mc), s->gpos, s->gv[src], s->gk[src], s->gstart, count, d_n,
                s->base, s->n, d_own, P.g, P.dist2, P.mc, s->edges, s->edge_slots, s->edge_cap, s->d_edge_count);
     return 0;
 }

@@ -120,6 +120,10 @@ struct GraphList {
     __device__ __forceinline__ float& D(int k) { return d2[k * CF_GRAPH_THREADS]; }
 };
 
+__host__ __device__ constexpr size_t graph_list_bytes(int max_conn) { // [3][2*maxConn][threads]: id, position, d2
+    return (size_t)3 * 2 * max_conn * CF_GRAPH_THREADS * sizeof(int);
+}
+
 __global__ void __launch_bounds__(CF_GRAPH_THREADS)
 graph_kernel(const float4* __restrict__ gpos, const uint32_t* __restrict__ gvals, const uint32_t* __restrict__ gkeys,
              const int* __restrict__ gstart, int nq_upper, const int* __restrict__ d_nq, int own_first, int n_own_host,
