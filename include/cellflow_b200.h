@@ -297,6 +297,11 @@ int cf_download_cell_keys(cf_sim* sim, uint32_t* keys, int32_t* ids, int capacit
  *   "force_kernel"   0 auto | 1 one thread per particle | 2 tile kernel, generation 3 |
  *                    3 tile kernel, generation 4 (box prefilter, type-sorted j stream)
  *   "graph_kernel"   0 auto | 1 one thread per particle | 2 one warp per particle (dense states)
+ *   "t4_stage"       staging of the j chunks in the generation-4 tile kernel, all bit-identical: 4 (default) box prefilter
+ *                    on the registers, live quads stored compacted | 0 every quad stored | 1 cp.async.bulk + mbarrier from
+ *                    SoA planes | 2 precomputed quad boxes | 3 SoA planes through registers (1, 3: per-type radii only)
+ *   "t4_ctas_per_sm", "count_blocks"   experiment knobs of the same kernel: fewer resident CTAs; instrumented build that
+ *                    fills cf_stats.exact_tested_pairs / evaluated_pair_lanes
  *   "cuda_graphs"    1 (default): single-GPU step and graph build replay captured CUDA graphs
  *   "timing"         0 off | 1 events between the phases of a step | 2 events around whole steps
  *   "max_cells_per_particle"   upper bound of grid cells per particle (default 16)
