@@ -1504,15 +1504,19 @@ static int graph_make_plan(cf_sim* s, float dist, int mc, GraphPlan& P) {
     P.mc = mc;
     P.dist2 = dist * dist;
     // kernel choice from the occupancy of the PREVIOUS build (read back with its edge count, so no
-    // extra synchronisation): ~27 * mean occupancy candidates per particle; above ~250 the
-    // warp-per-particle kernel wins (spawn cube, clustered states), below it thread-per-particle
+    // extra synchronisation): ~27 * mean occupancy candidates per particle.  The warp-per-particle kernel wins
+    // when a particle has hundreds of candidates AND there are too few particles for one thread each to fill
+    // the GPU (tools/graph_crossover.py, the reference's spawn cube: 0.129 vs 0.163 ms at 25 k particles, 0.177 vs
+    // 0.194 at 50 k, but 0.299 vs 0.278 at 100 k and 3.70 vs 3.25 at 800 k since the thread-per-particle kernel
+    // keeps unordered lists); otherwise thread-per-particle
     P.gkernel = s->opt_graph_kernel;
     // (asynchronous builds never read the count back: the pinned mirror of an earlier build's occupancy stands in;
     //  both kernels produce the same edge set, so the choice may depend on timing)
     double occ = s->graph_mean_occ;
     if (s->h_graph_occ_pin && s->graph_plan_count > 0 && s->n > 0)
         occ = std::max(occ, (double)*s->h_graph_occ_pin / (double)s->graph_plan_count);
-    if (P.gkernel == 0) P.gkernel = 27.0 * occ >= 250.0 ? 2 : 1;
+    const int n_graph = s->slab ? s->n : P.count;
+    if (P.gkernel == 0) P.gkernel = (27.0 * occ >= 250.0 && n_graph < 75000) ? 2 : 1;
     return 0;
 }
 
